@@ -1,0 +1,107 @@
+// Internal declarations shared by the translation units of libbugcar_b200.so.
+// Not part of the ABI (see include/bugcar_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+namespace bc {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ packed layers
+// One convolution (+ folded batch norm + activation slope) for the CUDA-core kernels.
+// w is [tap][cin][cout] fp32 (values rounded to bf16 in BC_PREC_BF16 so that both the
+// CUDA-core and the tcgen05 kernels see identical operands), bias/alpha are [cout].
+struct ConvP {
+  float* w = nullptr;
+  float* bias = nullptr;
+  float* alpha = nullptr;    // PReLU slope per output channel (0 = ReLU, 1 = identity)
+  int cin = 0, cout = 0, ntaps = 0;
+};
+
+// tcgen05 operand pack for one fused regular bottleneck (bf16, K-major core-matrix
+// layout, see enet_umma.cu)
+struct UmmaP {
+  bf16* w1 = nullptr;   // [CI][C]
+  bf16* w2 = nullptr;   // [taps][CI][CI]
+  bf16* w3 = nullptr;   // [C][CI]
+  void* blob = nullptr; // single device allocation holding the three + params
+  size_t blob_bytes = 0;
+};
+
+struct Bottleneck {
+  std::string name;
+  int kind;                  // 0 down, 1 regular, 2 asymmetric, 3 up
+  int cin, cout, ci, dilation;
+  ConvP c1, c2, c2b, c3, cm; // proj / mid / mid-second (asym) / expand / main (up)
+  float* alpha_out = nullptr;
+  UmmaP umma;
+};
+
+struct Taps { int8_t dy[9]; int8_t dx[9]; };
+
+struct Lut256 { uint8_t v[256]; };
+
+// ------------------------------------------------------------------ BEV parameters
+struct BevGeom {            // kernel parameter block for K9 (passed by value)
+  double Mi[9];             // inverse homography (dst -> src), fp64 (cv::invert)
+  int bw0;                  // OpenCV warp block width (coordinate association)
+  int in_rows, in_cols;     // label map
+  int warp_w, warp_h;
+  int occ_w_px, occ_h_px;   // template size
+  int wl, wt, gl, gt;       // crop / paste offsets (bev.py:183-189)
+  int crop_w, crop_h;
+  int Wc, Hc;               // grid cells
+  int binary, ros_layout;
+};
+
+// ------------------------------------------------------------------ launchers (enet_simt.cu)
+struct Net;   // forward (api.cu)
+
+template <typename T>
+void launch_initial(const void* x, int kind, int B, T* out, const float* w, const float* g,
+                    const float* b, const float* alpha, const float* lut, cudaStream_t s);
+template <typename T>
+void launch_down_a(const T* x, int B, int H, int W, int cin, int ci, T* pooled, uint8_t* idx,
+                   T* e1, const ConvP& c1, cudaStream_t s);
+template <typename T>
+void launch_conv(const T* in, T* out, const T* res, int res_ch, const ConvP& c,
+                 const float* alpha_out, int B, int H, int W, const Taps& taps, cudaStream_t s);
+template <typename T>
+void launch_up_b(const T* x, const T* e1, const uint8_t* idx, T* out, const Bottleneck& bn,
+                 int B, int H, int W, cudaStream_t s);
+template <typename T>
+void launch_fullconv(const T* x, int B, int C, const float* w, float* logits, uint8_t* labels,
+                     const Lut256* lut, cudaStream_t s);
+
+// ------------------------------------------------------------------ launchers (enet_umma.cu)
+// Fused regular bottleneck (1x1 -> 3x3 -> 1x1 + residual) on tcgen05; bf16 only.
+// Returns false when the shape is not covered (caller falls back to CUDA-core kernels).
+bool umma_supported(const Bottleneck& bn);
+void umma_pack(Bottleneck& bn, const std::vector<float>& w1, const std::vector<float>& w2,
+               const std::vector<float>& w3);   // folded fp32 [tap][cin][cout] inputs
+void launch_umma_bottleneck(const bf16* x, bf16* y, const Bottleneck& bn, int B, int H, int W,
+                            int num_sms, cudaStream_t s);
+
+// ------------------------------------------------------------------ launchers (prepost.cu)
+struct ResizeTab {          // device tables for cv2.resize INTER_LINEAR, one (h,w)
+  int src_h = 0, src_w = 0;
+  int mode = 0;             // 0 identity, 1 area 2x2, 2 linear fixed-point
+  int* x0 = nullptr; int* x1 = nullptr; int* a0 = nullptr; int* a1 = nullptr;   // [512]
+  int* y0 = nullptr; int* y1 = nullptr; int* b0 = nullptr; int* b1 = nullptr;   // [256]
+  void* blob = nullptr;
+};
+void launch_resize(const uint8_t* src, int h, int w, int B, uint8_t* dst, const ResizeTab& t,
+                   cudaStream_t s);
+void launch_preprocess(const uint8_t* bgr256, int B, void* out, int out_f64, const double* lut64,
+                       cudaStream_t s);
+void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lut256& lut,
+                       uint8_t* labels, cudaStream_t s);
+void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, const int* xi, const int* yi,
+                    int8_t* grids, cudaStream_t s);
+
+}  // namespace bc

@@ -1,0 +1,237 @@
+// Pre/post-processing kernels of the hot path (CUDA cores; integer / fp64 work).
+//
+//   K1  k_resize        cv2.resize(bgr,(512,256)) bit-exact            models.py:87
+//       k_preprocess    BGR->RGB, (u/256-mean)/std, HWC->CHW           models.py:89-94
+//   K8' k_argmax_lut    tf.math.argmax(axis=1) + class LUT             models.py:55-58,67 / 78-81
+//   K9  k_occgrid       warpPerspective + crop/paste + 3x3 open + nearest resize + int8 map,
+//                       one kernel, no intermediate image              bev.py:166-246 / 97-144
+//
+// All of it is byte/integer arithmetic with fp64 coordinates, bound by HBM/L2 traffic
+// (K9: 131 072 B labels in, Hc*Wc B out per frame).  Semantics follow OpenCV 4.x as
+// restated (and pinned against cv2) in oracle/cv_ops.py.
+#include "internal.h"
+
+namespace bc {
+
+static constexpr int NET_W = 512, NET_H = 256;
+
+// ------------------------------------------------------------------------------ K1
+// mode 0 identity copy; mode 1 area 2x2: (a+b+c+d+2)>>2 (cv::resize swaps INTER_LINEAR
+// for INTER_AREA when both scales are exactly 2); mode 2 the 11-bit fixed-point separable
+// bilinear kernel (HResizeLinear / VResizeLinear, INTER_RESIZE_COEF_BITS = 11).
+__global__ void __launch_bounds__(256)
+k_resize(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst,
+         ResizeTab t, int total_px) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;   // destination pixel over B*256*512
+  if (p >= total_px) return;
+  int x = p % NET_W;
+  int y = (p / NET_W) % NET_H;
+  int n = p / (NET_W * NET_H);
+  const uint8_t* s = src + (size_t)n * sh * sw * 3;
+  uint8_t* d = dst + (size_t)p * 3;
+  if (t.mode == 1) {
+    const uint8_t* r0 = s + ((size_t)(2 * y) * sw + 2 * x) * 3;
+    const uint8_t* r1 = r0 + (size_t)sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      d[c] = (uint8_t)((r0[c] + r0[3 + c] + r1[c] + r1[3 + c] + 2) >> 2);
+    return;
+  }
+  int x0 = t.x0[x], x1 = t.x1[x], a0 = t.a0[x], a1 = t.a1[x];
+  int y0 = t.y0[y], y1 = t.y1[y], b0 = t.b0[y], b1 = t.b1[y];
+  const uint8_t* r0 = s + (size_t)y0 * sw * 3;
+  const uint8_t* r1 = s + (size_t)y1 * sw * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int S0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+    int S1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+    int v = (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2;
+    d[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+void launch_resize(const uint8_t* src, int h, int w, int B, uint8_t* dst, const ResizeTab& t,
+                   cudaStream_t s) {
+  if (t.mode == 0) {
+    cudaMemcpyAsync(dst, src, (size_t)B * NET_H * NET_W * 3, cudaMemcpyDeviceToDevice, s);
+    return;
+  }
+  int total = B * NET_H * NET_W;
+  k_resize<<<(total + 255) / 256, 256, 0, s>>>(src, h, w, dst, t, total);
+}
+
+// ----------------------------------------------------------------- preprocess (API)
+// out[n][c][y][x] = lut64[bgr[n][y][x][2-c]][c]; lut64 is the fp64 table
+// ((u/256.0)-mean[c])/std[c] computed on the host exactly as numpy does (models.py:91).
+template <typename OUT>
+__global__ void __launch_bounds__(256)
+k_preprocess(const uint8_t* __restrict__ bgr, OUT* __restrict__ out,
+             const double* __restrict__ lut64, int total_px) {
+  __shared__ double slut[256 * 3];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) slut[i] = lut64[i];
+  __syncthreads();
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_px) return;
+  int n = p / (NET_W * NET_H);
+  int yx = p % (NET_W * NET_H);
+  const uint8_t* s = bgr + (size_t)p * 3;
+  OUT* o = out + (size_t)n * 3 * NET_W * NET_H + yx;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[(size_t)c * NET_W * NET_H] = (OUT)slut[s[2 - c] * 3 + c];
+}
+
+void launch_preprocess(const uint8_t* bgr256, int B, void* out, int out_f64, const double* lut64,
+                       cudaStream_t s) {
+  int total = B * NET_H * NET_W;
+  if (out_f64)
+    k_preprocess<double><<<(total + 255) / 256, 256, 0, s>>>(bgr256, (double*)out, lut64, total);
+  else
+    k_preprocess<float><<<(total + 255) / 256, 256, 0, s>>>(bgr256, (float*)out, lut64, total);
+}
+
+// ------------------------------------------------------------------- argmax + LUT
+// logits NCHW fp32; first maximum wins (tf.math.argmax / np.argmax tie-break).
+__global__ void __launch_bounds__(256)
+k_argmax_lut(const float* __restrict__ logits, int C, int HW, Lut256 lut,
+             uint8_t* __restrict__ labels, int total_px) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total_px) return;
+  int n = p / HW, yx = p % HW;
+  const float* l = logits + (size_t)n * C * HW + yx;
+  float best = l[0];
+  int bi = 0;
+  for (int c = 1; c < C; ++c) {
+    float v = l[(size_t)c * HW];
+    if (v > best) { best = v; bi = c; }
+  }
+  labels[p] = lut.v[bi];
+}
+
+void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lut256& lut,
+                       uint8_t* labels, cudaStream_t s) {
+  int total = B * H * W;
+  k_argmax_lut<<<(total + 255) / 256, 256, 0, s>>>(logits, C, H * W, lut, labels, total);
+}
+
+// ------------------------------------------------------------------------------ K9
+// Value of the warped (label+1) image at destination pixel (x, y): OpenCV's
+// warpPerspective, INTER_LINEAR, BORDER_CONSTANT 0, 5-bit fixed-point weights.  The
+// fp64 association (block origin xb) and the absence of FMA contraction reproduce
+// WarpPerspectiveInvoker exactly (oracle/cv_ops.py warp_coords_fixed).
+__device__ __forceinline__ int warp_sample(const uint8_t* __restrict__ lab, const BevGeom& g,
+                                           int x, int y) {
+  int xb = (x / g.bw0) * g.bw0;
+  double dxb = (double)xb, dx1 = (double)(x - xb), dy = (double)y;
+  double X0 = __dadd_rn(__dadd_rn(__dmul_rn(g.Mi[0], dxb), __dmul_rn(g.Mi[1], dy)), g.Mi[2]);
+  double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(g.Mi[3], dxb), __dmul_rn(g.Mi[4], dy)), g.Mi[5]);
+  double W0 = __dadd_rn(__dadd_rn(__dmul_rn(g.Mi[6], dxb), __dmul_rn(g.Mi[7], dy)), g.Mi[8]);
+  double W = __dadd_rn(W0, __dmul_rn(g.Mi[6], dx1));
+  W = (W != 0.0) ? __ddiv_rn(32.0, W) : 0.0;
+  double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(g.Mi[0], dx1)), W);
+  double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(g.Mi[3], dx1)), W);
+  fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
+  fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
+  int X = __double2int_rn(fX);      // cvRound: round half to even
+  int Y = __double2int_rn(fY);
+  int sx = min(max(X >> 5, -32768), 32767);   // saturate_cast<short>
+  int sy = min(max(Y >> 5, -32768), 32767);
+  int ax = X & 31, ay = Y & 31;
+  int acc = 0;
+  const int rows = g.in_rows, cols = g.in_cols;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    int yy = sy + j;
+    int wy = j ? ay : 32 - ay;
+    if (yy < 0 || yy >= rows) continue;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int xx = sx + i;
+      int wx = i ? ax : 32 - ax;
+      if (xx < 0 || xx >= cols) continue;
+      int v = (lab[yy * cols + xx] + 1) & 255;   // np.add(segmap, 1) on uint8 (bev.py:177)
+      acc += v * wy * wx;
+    }
+  }
+  return (acc + 512) >> 10;
+}
+
+// template pixel (ty, tx): crop of the warped image pasted into a zero image
+// (bev.py:183-195)
+__device__ __forceinline__ int template_px(const uint8_t* __restrict__ lab, const BevGeom& g,
+                                           int tx, int ty) {
+  int cx = tx - g.gl, cy = ty - g.gt;
+  if (cx < 0 || cy < 0 || cx >= g.crop_w || cy >= g.crop_h) return 0;
+  return warp_sample(lab, g, cx + g.wl, cy + g.wt);
+}
+
+__device__ __forceinline__ bool is_occ(int v, int binary) {
+  return binary ? (v == 1) : (v == 1 || v == 3);   // bev.py:128 / bev.py:196
+}
+
+// One thread per grid cell.  The cell takes template pixel (yi[cy], xi[cx]) (nearest
+// resize); if that pixel is "occupied" the 3x3 opening decides whether it is a speck:
+//   opened(p) = OR_{q in N3(p)} AND_{r in N3(q)} occ(r)   (erode ignores pixels outside
+//   the template, dilate treats them as 0 -- OpenCV default border values)
+__global__ void __launch_bounds__(128)
+k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, const int* __restrict__ xi,
+          const int* __restrict__ yi, int8_t* __restrict__ grids) {
+  int cx = blockIdx.x * blockDim.x + threadIdx.x;
+  int cy = blockIdx.y;
+  int n = blockIdx.z;
+  if (cx >= g.Wc) return;
+  const uint8_t* lab = labels + (size_t)n * g.in_rows * g.in_cols;
+  int tx = xi[cx], ty = yi[cy];
+  int v = template_px(lab, g, tx, ty);
+  if (is_occ(v, g.binary)) {
+    // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i); outside = "ignore"
+    unsigned occ = 0, inside = 0;
+    for (int j = 0; j < 5; ++j) {
+      int y = ty - 2 + j;
+      if (y < 0 || y >= g.occ_h_px) continue;
+      for (int i = 0; i < 5; ++i) {
+        int x = tx - 2 + i;
+        if (x < 0 || x >= g.occ_w_px) continue;
+        unsigned bit = 1u << (j * 5 + i);
+        inside |= bit;
+        int u = (i == 2 && j == 2) ? v : template_px(lab, g, x, y);
+        if (is_occ(u, g.binary)) occ |= bit;
+      }
+    }
+    bool opened = false;
+#pragma unroll
+    for (int qj = 1; qj <= 3; ++qj)
+#pragma unroll
+      for (int qi = 1; qi <= 3; ++qi) {
+        unsigned qbit = 1u << (qj * 5 + qi);
+        if (!(inside & qbit)) continue;            // dilate: outside contributes 0
+        unsigned nb = 0;
+#pragma unroll
+        for (int rj = -1; rj <= 1; ++rj)
+#pragma unroll
+          for (int ri = -1; ri <= 1; ++ri) nb |= 1u << ((qj + rj) * 5 + (qi + ri));
+        // erode: every in-template neighbour must be occupied
+        if (((~occ) & inside & nb) == 0) opened = true;
+      }
+    if (!opened) v = 2;                             // bev.py:203-205
+  }
+  int out;
+  if (g.binary) {
+    int m = (v * 100) & 255;                        // uint8 * 100 (bev.py:139-142)
+    out = (m == 0) ? 255 : ((200 - m) & 255);       // bev.py:143-144
+  } else {
+    if (v == 3) v = 1;                              // bev.py:242
+    out = (v == 0) ? 255 : ((200 - ((v * 100) & 255)) & 255);   // bev.py:244-245
+  }
+  size_t cells = (size_t)g.Hc * g.Wc;
+  size_t o = g.ros_layout ? (size_t)(g.Wc - 1 - cx) * g.Hc + (g.Hc - 1 - cy)   // occgrid_to_ros.py:18-21
+                          : (size_t)cy * g.Wc + cx;
+  grids[(size_t)n * cells + o] = (int8_t)out;
+}
+
+void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, const int* xi, const int* yi,
+                    int8_t* grids, cudaStream_t s) {
+  dim3 grid((g.Wc + 127) / 128, g.Hc, B);
+  k_occgrid<<<grid, 128, 0, s>>>(labels, g, xi, yi, grids);
+}
+
+}  // namespace bc
