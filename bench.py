@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Headline benchmark: camera frame -> ENet -> class argmax/LUT -> BEV warp -> occupancy grid,
+frames/s (BASELINE.json metric), bs 256 per GPU, bf16, synthetic frames, random-init weights
+of the ENet architecture (pretrained_models/enet_synthetic_seed42.bcw).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One process per GPU (torchrun for N > 1).  A step = one pass of the hot path over one batch
+of 256 frames per GPU.  `value` = frames/s with inputs resident in HBM (bc_pipeline);
+`e2e` = the same through the host entry point (pinned host frames -> H2D -> graph -> D2H of
+the grids).  `roofline` = the dominant kernel, timed with CUDA events by the library's
+per-kernel profiler in a separate pass right after the timed region (same workload).
+`cpu_baseline` / `--impl reference` time the CPU restatement of the reference path
+(torch-fp32 ENet + OpenCV pre/post, what the reference's Python does minus TensorFlow,
+which is not installable here) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 256
+GRID = (10.0, 10.0, 0.1)
+CAL = "A"
+METRIC = "enet_frame_to_occupancy_grid_frames_per_s"
+N_INPUT_SETS = 4          # 4 x 100 MB of frames rotate through the steps (> 126 MB L2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_frames(rank, n_sets):
+    """frame i of rank r in set k: seed 1234 + k*100000 + r*BATCH + i.
+    Generating 1024 seeded frames with NumPy takes a while; build 32 per set and tile."""
+    from bugcar_image_segmentation_b200 import synth
+    sets = []
+    for k in range(n_sets):
+        base = synth.frames(32, 1234 + k * 100000 + rank * BATCH)
+        sets.append(np.ascontiguousarray(np.tile(base, (BATCH // 32, 1, 1, 1))))
+    return sets
+
+
+def cpu_reference_step(w, eps, frames, cal, torch_threads):
+    """the reference's per-frame path on the CPU: preprocess (models.py:84-95), ENet forward
+    (torch fp32 stand-in for sess.run, models.py:43-44), argmax + LUT (models.py:55-67),
+    create_occupancy_grid (bev.py:166-246, OpenCV back end)."""
+    from oracle import pre_oracle, enet_oracle, bev_oracle
+    ww, wh = cal["output image size"]
+    out = []
+    for f in frames:
+        x = pre_oracle.preprocess(f, backend="cv2")
+        lg = enet_oracle.forward(w, x, eps)
+        lab = pre_oracle.labels_from_logits(lg, pre_oracle.LUT_3WAY)
+        out.append(bev_oracle.occupancy_grid(lab[0], cal["bev matrix"], ww, wh, cal["cm_per_px"], *GRID, backend="cv2"))
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement on all host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from bugcar_image_segmentation_b200 import synth, weights as W
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with open(os.path.join(ROOT, "pretrained_models", "enet_synthetic_seed42.bcw"), "rb") as f:
+        w, nc, eps = W.unpack_flat(f.read())
+    cal = synth.calibration(CAL)
+    per_step = 4                                   # bounded sample of the 256-frame batch
+    frames = synth.frames(per_step, 1234)
+    for _ in range(args.warmup):
+        cpu_reference_step(w, eps, frames[:1], cal, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(w, eps, frames, cal, threads)
+    dt = time.perf_counter() - t0
+    fps = per_step * args.steps / dt
+    sample = f"{per_step} frames/step of the {BATCH}-frame batch, bs 1 per call as the reference's loop does"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"full pipeline frame->grid, calibration {CAL}, grid 10x10 m @ 0.1 m; CPU restatement "
+                               "(torch fp32 ENet + OpenCV pre/post); TensorFlow/Keras not installable here"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-tc", action="store_true")
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-latency", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from bugcar_image_segmentation_b200 import synth, sharding, weights as W
+    from bugcar_image_segmentation_b200.models import ENET
+    from bugcar_image_segmentation_b200.bev import bev_transform_tools
+    from bugcar_image_segmentation_b200.pipeline import FramePipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    B = args.batch
+
+    wpath = os.path.join(ROOT, "pretrained_models", "enet_synthetic_seed42.bcw")
+    model = ENET(wpath, device=local, max_batch=B, precision="bf16")
+    if args.chunk:
+        model.ctx.set_chunk(args.chunk)
+    if args.no_tc:
+        model.ctx.set_tensor_cores(0)
+    cal = synth.calibration(CAL)
+    bev = bev_transform_tools(cal["input image size"], cal["output image size"], cal["distance to target"],
+                              cal["tile_length"], cal["cm_per_px"], cal["yaw"], cal["is_laserscan"])
+    bev._bev_matrix = np.asarray(cal["bev matrix"]).reshape(3, 3)
+    pipe = FramePipeline(model, bev, *GRID)
+    Hc, Wc = pipe.Hc, pipe.Wc
+
+    host_sets = make_frames(rank, N_INPUT_SETS)
+    if B != BATCH:
+        host_sets = [s[:B] for s in host_sets]
+    pinned = [torch.from_numpy(s).pin_memory() for s in host_sets]
+    dev_sets = [p.cuda(non_blocking=True) for p in pinned]
+    d_grids = torch.empty((B, Hc, Wc), dtype=torch.int8, device="cuda")
+    pinned_out = torch.empty((world * B if rank == 0 else B, Hc, Wc), dtype=torch.int8).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        pipe.run_device(dev_sets[i % N_INPUT_SETS], d_grids)
+        if world > 1:
+            return sharding.gather_grids(d_grids, rank, world)
+        return d_grids
+
+    def step_e2e(i):
+        if world == 1:
+            model.ctx.pipeline_host(pinned[i % N_INPUT_SETS], 256, 512, B, pipe.lut, *GRID, 0, 0, pinned_out,
+                                    stream.cuda_stream)
+        else:
+            d = dev_sets[0]
+            d.copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
+            pipe.run_device(d, d_grids)
+            allg = sharding.gather_grids(d_grids, rank, world)
+            if rank == 0:
+                pinned_out.copy_(allg, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput
+    for i in range(args.warmup):
+        step_device(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = model.ctx.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = model.ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the host entry point
+    for i in range(args.warmup):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+    grids_check = pinned_out.numpy()[:B].copy()
+
+    # ---- per-kernel profile (events around every launch), rank 0 at any N
+    roofline, kernels = None, None
+    if rank == 0:
+        hbm, tf, which = peaks()
+        model.ctx.set_profile(True)
+        for i in range(max(2, min(args.steps, 5))):
+            pipe.run_device(dev_sets[i % N_INPUT_SETS], d_grids)
+        kernels = model.ctx.profile()
+        model.ctx.set_profile(False)
+        tot = sum(k["ms"] for k in kernels)
+        for k in kernels:
+            k["share"] = k["ms"] / tot
+            k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else 0.0
+            k["tflops"] = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
+        kernels.sort(key=lambda k: -k["ms"])
+        top = kernels[0]
+        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
+                    "frac": top["gbs"] / hbm, "traffic": None, "peak_source": which,
+                    "share_of_step": top["share"], "avg_launch_us": top["ms"] * 1e3 / top["launches"],
+                    "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
+                    "whole_path": {"algorithmic_gbs": sum(k["bytes"] for k in kernels) / (tot * 1e-3) / 1e9,
+                                   "frac": sum(k["bytes"] for k in kernels) / (tot * 1e-3) / 1e9 / hbm,
+                                   "tflops": sum(k["flops"] for k in kernels) / (tot * 1e-3) / 1e12}}
+
+    # ---- batch-1 streaming latency (BASELINE config 3) on rank 0 of a 1-GPU run
+    latency = None
+    if rank == 0 and world == 1 and not args.skip_latency:
+        one_in = torch.from_numpy(host_sets[0][:1].copy()).pin_memory()
+        one_out = torch.empty((1, Hc, Wc), dtype=torch.int8).pin_memory()
+        ts = []
+        for i in range(220):
+            one_in.numpy()[0, 0, 0, 0] = i % 251
+            t0 = time.perf_counter()
+            model.ctx.pipeline_host(one_in, 256, 512, 1, pipe.lut, *GRID, 0, 0, one_out, stream.cuda_stream)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts = np.array(ts[20:])
+        latency = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)),
+                   "mean_ms": float(ts.mean()), "frames": int(ts.size),
+                   "how": "bc_pipeline_host, bs 1, pinned host frame -> grid on host, wall clock"}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        with open(wpath, "rb") as f:
+            w, nc, eps = W.unpack_flat(f.read())
+        sample = host_sets[0][:6]
+        cpu_reference_step(w, eps, sample[:1], cal, threads)
+        t0 = time.perf_counter()
+        ref_grids = cpu_reference_step(w, eps, sample, cal, threads)
+        dt = time.perf_counter() - t0
+        same = float(np.mean([np.mean(ref_grids[i] == grids_check[i]) for i in range(len(sample))]))
+        cpu = {"value": len(sample) / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{len(sample)} frames of the batch, per-frame calls (torch fp32 ENet + OpenCV pre/post)",
+               "grid_cell_agreement_bf16_vs_cpu_fp32": same}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"full pipeline frame->ENet->argmax/LUT->BEV grid, bs {B} per GPU, 256x512 BGR frames, "
+                                   f"15 classes, calibration {CAL} (500x500 warp), grid 10x10 m @ 0.1 m",
+                       "weights": "enet_synthetic_seed42.bcw (random init, BN calibrated)",
+                       "l2": f"{N_INPUT_SETS} input sets x {B * 393216 / 1e6:.0f} MB rotate (> 126 MB L2)",
+                       "parallelism": f"frame-sharded dp{world}" + (", grids gathered to rank 0 (NCCL)" if world > 1 else ""),
+                       "chunk": args.chunk, "tensor_cores": not args.no_tc},
+            "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "latency_bs1": latency, "kernels": kernels,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

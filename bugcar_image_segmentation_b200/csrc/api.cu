@@ -1,0 +1,1097 @@
+// C ABI of libbugcar_b200.so (include/bugcar_b200.h): context, weight container parsing,
+// batch-norm folding, the ENet layer schedule, BEV geometry and the whole-path entry points.
+//
+// Reference call surface replaced (paths relative to the reference root):
+//   ENET.__init__            models.py:21-31     -> bc_create + bc_load_enet
+//   ENET.preprocess          models.py:84-95     -> bc_resize_bgr / bc_preprocess
+//   ENET.predict[_binary]    models.py:42-82     -> bc_enet_logits / bc_enet_labels / bc_argmax_lut
+//   bev_transform_tools      bev.py:13-41        -> bc_set_bev
+//   create_occupancy_grid*   bev.py:97-246       -> bc_occgrid
+//   the per-frame loop       README.md:18-20     -> bc_pipeline / bc_pipeline_host
+#include "internal.h"
+#include "../../include/bugcar_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <type_traits>
+
+using namespace bc;
+
+namespace {
+
+// ---------------------------------------------------------------- host-side conv pack
+struct HostConv {
+  std::vector<float> w, bias, alpha;   // [tap][cin][cout], [cout], [cout]
+  int cin = 0, cout = 0, ntaps = 0;
+};
+
+struct HostBlock {
+  std::string name;
+  int kind = 0;                        // 0 down, 1 regular, 2 asymmetric, 3 up
+  int cin = 0, cout = 0, ci = 0, dilation = 1;
+  HostConv c1, c2, c2b, c3, cm;
+  std::vector<float> alpha_out;
+};
+
+struct Tensor {
+  const float* data = nullptr;
+  int ndim = 0;
+  int dims[4] = {0, 0, 0, 0};
+  size_t count() const {
+    size_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= (size_t)dims[i];
+    return n;
+  }
+};
+
+struct GraphKey {
+  const void* in; const void* out; const void* labels;
+  int h, w, B, binary, ros, pad_;
+  double w_m, h_m, cell_m;
+  uint8_t lut[256];
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+
+struct ProfRec {
+  const char* name;
+  double bytes, flops;      // algorithmic bytes moved / flops of this launch
+  cudaEvent_t start, stop;
+};
+
+inline float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+}  // namespace
+
+// ----------------------------------------------------------------------- the context
+struct bc_ctx {
+  int device = 0;
+  int max_batch = 0;
+  int num_sms = 0;
+  std::string err;
+  long long launches = 0;
+
+  int precision = BC_PREC_BF16;
+  int chunk = 0;            // 0 = default
+  int tensor_cores = 1;
+  int use_graphs = 1;
+
+  // ---- network (host copies, folded, fp32)
+  bool net_loaded = false;
+  int num_classes = 0;
+  float bn_eps = 1e-5f;
+  std::vector<float> h_init_w, h_init_g, h_init_b, h_init_a;   // [27][13], [16] x3
+  std::vector<HostBlock> h_blocks;
+  std::vector<float> h_full_w;                                  // [9][16][CP]
+  // ---- network (device)
+  std::vector<void*> dev_allocs;      // weight allocations
+  float *d_init_w = nullptr, *d_init_g = nullptr, *d_init_b = nullptr, *d_init_a = nullptr;
+  std::vector<Bottleneck> blocks;
+  float* d_full_w = nullptr;
+  // normalisation LUTs (models.py:91): [256][3] RGB order
+  float* d_lut32 = nullptr;
+  double* d_lut64 = nullptr;
+
+  // ---- activation scratch
+  int scratch_frames = 0, scratch_esz = 0;
+  void *bufX = nullptr, *bufY = nullptr, *bufP = nullptr, *bufE1 = nullptr, *bufE2 = nullptr;
+  uint8_t *idx1 = nullptr, *idx2 = nullptr;
+  uint8_t* d_labels = nullptr;        // [max_batch][256][512]
+  uint8_t* d_resized = nullptr;       // [max_batch][256][512][3]
+  uint8_t* d_frames_in = nullptr;     // staging for *_host calls
+  size_t frames_in_bytes = 0;
+  int8_t* d_grids_out = nullptr;
+  size_t grids_out_bytes = 0;
+
+  // ---- BEV
+  bool bev_set = false;
+  double M[9], Mi[9];
+  int in_rows = 0, in_cols = 0, warp_w = 0, warp_h = 0;
+  double cm_per_px = 1.0;
+
+  // ---- resize tables, keyed by source size
+  std::map<std::pair<int, int>, ResizeTab> resize_tabs;
+
+  // ---- multi-GPU gather
+  int8_t* gather_base = nullptr;
+  int rank = 0, world = 1;
+
+  // ---- CUDA graphs of bc_pipeline[_host]
+  std::vector<GraphEntry> graphs;
+
+  // ---- per-kernel profiling (bc_set_profile): one event pair per launch
+  int profiling = 0;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  std::string prof_json;
+};
+
+static std::string g_create_err;
+
+namespace {
+
+int fail(bc_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define CU(expr)                                                                     \
+  do {                                                                               \
+    cudaError_t e_ = (expr);                                                         \
+    if (e_ != cudaSuccess)                                                           \
+      return fail(c, BC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+int check_launch(bc_ctx* c, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return BC_OK;
+}
+
+// Every kernel launch goes through L(): counts it and, in profiling mode, brackets it with
+// a CUDA event pair on the launching stream and records its algorithmic bytes / flops.
+cudaEvent_t prof_event(bc_ctx* c) {
+  cudaEvent_t e;
+  if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+template <typename F>
+inline void L(bc_ctx* c, const char* name, double bytes, double flops, cudaStream_t s, F&& launch) {
+  c->launches++;
+  if (!c->profiling) { launch(); return; }
+  ProfRec r{name, bytes, flops, prof_event(c), prof_event(c)};
+  cudaEventRecord(r.start, s);
+  launch();
+  cudaEventRecord(r.stop, s);
+  c->prof.push_back(r);
+}
+
+// ----------------------------------------------------------- weight container parsing
+// BCENETW1 layout: see bugcar_image_segmentation_b200/weights.py
+struct Container {
+  std::map<std::string, Tensor> t;
+  int num_classes = 0;
+  float bn_eps = 1e-5f;
+};
+
+int parse_container(bc_ctx* c, const void* blob, size_t n, Container& out) {
+  const uint8_t* p = (const uint8_t*)blob;
+  if (n < 24 || memcmp(p, "BCENETW1", 8) != 0) return fail(c, BC_ERR_FORMAT, "not a BCENETW1 weight container");
+  uint32_t nt, nc, rsv;
+  float eps;
+  memcpy(&nt, p + 8, 4); memcpy(&nc, p + 12, 4); memcpy(&eps, p + 16, 4); memcpy(&rsv, p + 20, 4);
+  const size_t ent = 96 + 4 + 16 + 8;
+  size_t data0 = 24 + (size_t)nt * ent;
+  data0 += (64 - data0 % 64) % 64;
+  if (data0 > n) return fail(c, BC_ERR_FORMAT, "truncated weight container (table)");
+  out.num_classes = (int)nc;
+  out.bn_eps = eps;
+  for (uint32_t i = 0; i < nt; ++i) {
+    const uint8_t* e = p + 24 + (size_t)i * ent;
+    char name[97];
+    memcpy(name, e, 96); name[96] = 0;
+    uint32_t ndim, d[4];
+    uint64_t off;
+    memcpy(&ndim, e + 96, 4); memcpy(d, e + 100, 16); memcpy(&off, e + 116, 8);
+    if (ndim > 4) return fail(c, BC_ERR_FORMAT, std::string(name) + ": ndim > 4");
+    Tensor t;
+    t.ndim = (int)ndim;
+    for (int k = 0; k < 4; ++k) t.dims[k] = (int)d[k];
+    size_t cnt = t.count();
+    if (data0 + off + cnt * 4 > n) return fail(c, BC_ERR_FORMAT, std::string(name) + ": data out of bounds");
+    if ((data0 + off) % 4 != 0) return fail(c, BC_ERR_FORMAT, std::string(name) + ": misaligned data");
+    t.data = (const float*)(p + data0 + off);
+    out.t[name] = t;
+  }
+  return BC_OK;
+}
+
+const Tensor* find(const Container& ct, const std::string& name) {
+  auto it = ct.t.find(name);
+  return it == ct.t.end() ? nullptr : &it->second;
+}
+
+int need(bc_ctx* c, const Container& ct, const std::string& name, int ndim, const int* dims, const Tensor** out) {
+  const Tensor* t = find(ct, name);
+  if (!t) return fail(c, BC_ERR_FORMAT, "missing tensor " + name);
+  bool ok = t->ndim == ndim;
+  for (int i = 0; ok && i < ndim; ++i) ok = t->dims[i] == dims[i];
+  if (!ok) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: unexpected shape (%d dims: %d,%d,%d,%d)", name.c_str(), t->ndim,
+             t->dims[0], t->dims[1], t->dims[2], t->dims[3]);
+    return fail(c, BC_ERR_FORMAT, buf);
+  }
+  *out = t;
+  return BC_OK;
+}
+
+// batch-norm scale/shift: g = gamma / sqrt(var + eps), b = beta - mean * g
+int bn_fold(bc_ctx* c, const Container& ct, const std::string& p, int ch, std::vector<double>& g, std::vector<double>& b) {
+  const Tensor *tw, *tb, *tm, *tv;
+  int d[1] = {ch};
+  int r;
+  if ((r = need(c, ct, p + ".weight", 1, d, &tw))) return r;
+  if ((r = need(c, ct, p + ".bias", 1, d, &tb))) return r;
+  if ((r = need(c, ct, p + ".running_mean", 1, d, &tm))) return r;
+  if ((r = need(c, ct, p + ".running_var", 1, d, &tv))) return r;
+  g.resize(ch); b.resize(ch);
+  for (int i = 0; i < ch; ++i) {
+    // the oracle evaluates batch_norm in fp32: keep the fp32 rsqrt argument
+    double inv = 1.0 / std::sqrt((double)(float)(tv->data[i] + ct.bn_eps));
+    g[i] = (double)tw->data[i] * inv;
+    b[i] = (double)tb->data[i] - (double)tm->data[i] * g[i];
+  }
+  return BC_OK;
+}
+
+// activation slopes: missing tensor = ReLU (slope 0), 1 element = shared PReLU, ch elements = per channel
+int act_alpha(bc_ctx* c, const Container& ct, const std::string& name, int ch, std::vector<float>& a) {
+  a.assign(ch, 0.f);
+  const Tensor* t = find(ct, name + ".weight");
+  if (!t) return BC_OK;
+  size_t n = t->count();
+  if (n == 1) { for (int i = 0; i < ch; ++i) a[i] = t->data[0]; return BC_OK; }
+  if ((int)n == ch) { for (int i = 0; i < ch; ++i) a[i] = t->data[i]; return BC_OK; }
+  return fail(c, BC_ERR_FORMAT, name + ".weight: PReLU slope count matches neither 1 nor the channel count");
+}
+
+// conv (cout,cin,kh,kw) [transposed: (cin,cout,kh,kw)] + BN -> [tap][cin][cout] folded.
+// act: "" = identity (slope 1), else activation tensor prefix.
+int fold_conv(bc_ctx* c, const Container& ct, const std::string& conv, const std::string& bn,
+              const std::string& act, bool has_act, int cin, int cout, int kh, int kw, bool transposed, HostConv& out) {
+  const Tensor* w;
+  int d[4] = {transposed ? cin : cout, transposed ? cout : cin, kh, kw};
+  int r;
+  if ((r = need(c, ct, conv + ".weight", 4, d, &w))) return r;
+  std::vector<double> g, b;
+  if ((r = bn_fold(c, ct, bn, cout, g, b))) return r;
+  out.cin = cin; out.cout = cout; out.ntaps = kh * kw;
+  out.w.resize((size_t)kh * kw * cin * cout);
+  out.bias.resize(cout);
+  for (int o = 0; o < cout; ++o) out.bias[o] = (float)b[o];
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx)
+      for (int i = 0; i < cin; ++i)
+        for (int o = 0; o < cout; ++o) {
+          size_t src = transposed ? (((size_t)i * cout + o) * kh + ky) * kw + kx
+                                  : (((size_t)o * cin + i) * kh + ky) * kw + kx;
+          out.w[((size_t)(ky * kw + kx) * cin + i) * cout + o] = (float)((double)w->data[src] * g[o]);
+        }
+  if (has_act) return act_alpha(c, ct, act, cout, out.alpha);
+  out.alpha.assign(cout, 1.f);   // identity
+  return BC_OK;
+}
+
+struct BlockSpec { const char* name; int kind; int a, b; };
+// canonical ENet encoder/decoder (weights.py ENET_BLOCKS)
+const BlockSpec kBlocks[] = {
+    {"downsample1_0", 0, 16, 64},
+    {"regular1_1", 1, 64, 1}, {"regular1_2", 1, 64, 1}, {"regular1_3", 1, 64, 1}, {"regular1_4", 1, 64, 1},
+    {"downsample2_0", 0, 64, 128},
+    {"regular2_1", 1, 128, 1}, {"dilated2_2", 1, 128, 2}, {"asymmetric2_3", 2, 128, 1}, {"dilated2_4", 1, 128, 4},
+    {"regular2_5", 1, 128, 1}, {"dilated2_6", 1, 128, 8}, {"asymmetric2_7", 2, 128, 1}, {"dilated2_8", 1, 128, 16},
+    {"regular3_0", 1, 128, 1}, {"dilated3_1", 1, 128, 2}, {"asymmetric3_2", 2, 128, 1}, {"dilated3_3", 1, 128, 4},
+    {"regular3_4", 1, 128, 1}, {"dilated3_5", 1, 128, 8}, {"asymmetric3_6", 2, 128, 1}, {"dilated3_7", 1, 128, 16},
+    {"upsample4_0", 3, 128, 64},
+    {"regular4_1", 1, 64, 1}, {"regular4_2", 1, 64, 1},
+    {"upsample5_0", 3, 64, 16},
+    {"regular5_1", 1, 16, 1},
+};
+
+int build_host_net(bc_ctx* c, const Container& ct) {
+  int r;
+  c->num_classes = ct.num_classes;
+  c->bn_eps = ct.bn_eps;
+  if (ct.num_classes < 1 || ct.num_classes > 32) return fail(c, BC_ERR_FORMAT, "num_classes must be in [1, 32]");
+  // initial block: raw conv weights, BN as a per-channel affine on all 16 channels
+  {
+    const Tensor* w;
+    int d[4] = {13, 3, 3, 3};
+    if ((r = need(c, ct, "initial_block.main_branch.weight", 4, d, &w))) return r;
+    c->h_init_w.resize(27 * 13);
+    for (int o = 0; o < 13; ++o)
+      for (int ch = 0; ch < 3; ++ch)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            c->h_init_w[((ch * 3 + ky) * 3 + kx) * 13 + o] = w->data[((o * 3 + ch) * 3 + ky) * 3 + kx];
+    std::vector<double> g, b;
+    if ((r = bn_fold(c, ct, "initial_block.batch_norm", 16, g, b))) return r;
+    c->h_init_g.resize(16); c->h_init_b.resize(16);
+    for (int i = 0; i < 16; ++i) { c->h_init_g[i] = (float)g[i]; c->h_init_b[i] = (float)b[i]; }
+    if ((r = act_alpha(c, ct, "initial_block.out_activation", 16, c->h_init_a))) return r;
+  }
+  c->h_blocks.clear();
+  for (const BlockSpec& s : kBlocks) {
+    HostBlock hb;
+    hb.name = s.name;
+    hb.kind = s.kind;
+    std::string n = s.name;
+    if (s.kind == 0) {          // downsample: cin -> cout, internal cin/4
+      hb.cin = s.a; hb.cout = s.b; hb.ci = s.a / 4;
+      if ((r = fold_conv(c, ct, n + ".ext_conv1.0", n + ".ext_conv1.1", n + ".ext_conv1.2", true, hb.cin, hb.ci, 2, 2, false, hb.c1))) return r;
+      if ((r = fold_conv(c, ct, n + ".ext_conv2.0", n + ".ext_conv2.1", n + ".ext_conv2.2", true, hb.ci, hb.ci, 3, 3, false, hb.c2))) return r;
+      if ((r = fold_conv(c, ct, n + ".ext_conv3.0", n + ".ext_conv3.1", n + ".ext_conv3.2", true, hb.ci, hb.cout, 1, 1, false, hb.c3))) return r;
+    } else if (s.kind == 1 || s.kind == 2) {
+      hb.cin = hb.cout = s.a; hb.ci = s.a / 4; hb.dilation = s.b;
+      if ((r = fold_conv(c, ct, n + ".ext_conv1.0", n + ".ext_conv1.1", n + ".ext_conv1.2", true, hb.cin, hb.ci, 1, 1, false, hb.c1))) return r;
+      if (s.kind == 1) {
+        if ((r = fold_conv(c, ct, n + ".ext_conv2.0", n + ".ext_conv2.1", n + ".ext_conv2.2", true, hb.ci, hb.ci, 3, 3, false, hb.c2))) return r;
+      } else {
+        if ((r = fold_conv(c, ct, n + ".ext_conv2.0", n + ".ext_conv2.1", n + ".ext_conv2.2", true, hb.ci, hb.ci, 5, 1, false, hb.c2))) return r;
+        if ((r = fold_conv(c, ct, n + ".ext_conv2.3", n + ".ext_conv2.4", n + ".ext_conv2.5", true, hb.ci, hb.ci, 1, 5, false, hb.c2b))) return r;
+      }
+      if ((r = fold_conv(c, ct, n + ".ext_conv3.0", n + ".ext_conv3.1", n + ".ext_conv3.2", true, hb.ci, hb.cout, 1, 1, false, hb.c3))) return r;
+    } else {                    // upsample: cin -> cout, internal cin/4
+      hb.cin = s.a; hb.cout = s.b; hb.ci = s.a / 4;
+      if ((r = fold_conv(c, ct, n + ".main_conv1.0", n + ".main_conv1.1", "", false, hb.cin, hb.cout, 1, 1, false, hb.cm))) return r;
+      if ((r = fold_conv(c, ct, n + ".ext_conv1.0", n + ".ext_conv1.1", n + ".ext_conv1.2", true, hb.cin, hb.ci, 1, 1, false, hb.c1))) return r;
+      if ((r = fold_conv(c, ct, n + ".ext_tconv1", n + ".ext_tconv1_bnorm", n + ".ext_tconv1_activation", true, hb.ci, hb.ci, 2, 2, true, hb.c2))) return r;
+      if ((r = fold_conv(c, ct, n + ".ext_conv2.0", n + ".ext_conv2.1", "", false, hb.ci, hb.cout, 1, 1, false, hb.c3))) return r;
+    }
+    if ((r = act_alpha(c, ct, n + ".out_activation", hb.cout, hb.alpha_out))) return r;
+    c->h_blocks.push_back(std::move(hb));
+  }
+  {
+    const Tensor* w;
+    int C = ct.num_classes;
+    int d[4] = {16, C, 3, 3};
+    if ((r = need(c, ct, "transposed_conv.weight", 4, d, &w))) return r;
+    int cp = C <= 16 ? 16 : 32;
+    c->h_full_w.assign((size_t)9 * 16 * cp, 0.f);
+    for (int k = 0; k < 16; ++k)
+      for (int o = 0; o < C; ++o)
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            c->h_full_w[((size_t)(ky * 3 + kx) * 16 + k) * cp + o] = w->data[(((size_t)k * C + o) * 3 + ky) * 3 + kx];
+  }
+  return BC_OK;
+}
+
+// ------------------------------------------------------------------- device upload
+void free_net(bc_ctx* c) {
+  for (void* p : c->dev_allocs) cudaFree(p);
+  c->dev_allocs.clear();
+  c->blocks.clear();
+  c->d_init_w = c->d_init_g = c->d_init_b = c->d_init_a = c->d_full_w = nullptr;
+}
+
+int upload_vec(bc_ctx* c, const std::vector<float>& v, bool round_bf16, float** out) {
+  std::vector<float> tmp;
+  const float* src = v.data();
+  if (round_bf16) {
+    tmp.resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) tmp[i] = bf16_round(v[i]);
+    src = tmp.data();
+  }
+  float* d = nullptr;
+  CU(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  c->dev_allocs.push_back(d);
+  CU(cudaMemcpy(d, src, v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return BC_OK;
+}
+
+int upload_conv(bc_ctx* c, const HostConv& h, bool bf, ConvP& p) {
+  if (h.ntaps == 0) return BC_OK;
+  int r;
+  p.cin = h.cin; p.cout = h.cout; p.ntaps = h.ntaps;
+  if ((r = upload_vec(c, h.w, bf, &p.w))) return r;
+  if ((r = upload_vec(c, h.bias, false, &p.bias))) return r;
+  if ((r = upload_vec(c, h.alpha, false, &p.alpha))) return r;
+  return BC_OK;
+}
+
+void invalidate_graphs(bc_ctx* c) {
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
+}
+
+int upload_net(bc_ctx* c) {
+  invalidate_graphs(c);
+  free_net(c);
+  const bool bf = c->precision == BC_PREC_BF16;
+  int r;
+  // The initial block and the head read fp32 weights in both modes, except that bf16 mode
+  // rounds the head's weights (its input is bf16 and the oracle's emulation does the same).
+  if ((r = upload_vec(c, c->h_init_w, false, &c->d_init_w))) return r;
+  if ((r = upload_vec(c, c->h_init_g, false, &c->d_init_g))) return r;
+  if ((r = upload_vec(c, c->h_init_b, false, &c->d_init_b))) return r;
+  if ((r = upload_vec(c, c->h_init_a, false, &c->d_init_a))) return r;
+  if ((r = upload_vec(c, c->h_full_w, bf, &c->d_full_w))) return r;
+  for (const HostBlock& hb : c->h_blocks) {
+    Bottleneck b;
+    b.name = hb.name; b.kind = hb.kind; b.cin = hb.cin; b.cout = hb.cout; b.ci = hb.ci; b.dilation = hb.dilation;
+    if ((r = upload_conv(c, hb.c1, bf, b.c1))) return r;
+    if ((r = upload_conv(c, hb.c2, bf, b.c2))) return r;
+    if ((r = upload_conv(c, hb.c2b, bf, b.c2b))) return r;
+    if ((r = upload_conv(c, hb.c3, bf, b.c3))) return r;
+    if ((r = upload_conv(c, hb.cm, bf, b.cm))) return r;
+    if ((r = upload_vec(c, hb.alpha_out, false, &b.alpha_out))) return r;
+    c->blocks.push_back(b);
+  }
+  return BC_OK;
+}
+
+// ------------------------------------------------------------------------- scratch
+void free_scratch(bc_ctx* c) {
+  void** ps[] = {&c->bufX, &c->bufY, &c->bufP, &c->bufE1, &c->bufE2, (void**)&c->idx1, (void**)&c->idx2};
+  for (void** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+  c->scratch_frames = 0;
+}
+
+int chunk_frames(const bc_ctx* c) {
+  int ch = c->chunk > 0 ? c->chunk : 32;
+  return std::min(ch, c->max_batch);
+}
+
+int ensure_scratch(bc_ctx* c) {
+  int frames = chunk_frames(c);
+  int esz = c->precision == BC_PREC_BF16 ? 2 : 4;
+  if (c->scratch_frames == frames && c->scratch_esz == esz) return BC_OK;
+  invalidate_graphs(c);
+  free_scratch(c);
+  const size_t big = 524288, small = 131072;   // elements per frame
+  CU(cudaMalloc(&c->bufX, big * esz * frames));
+  CU(cudaMalloc(&c->bufY, big * esz * frames));
+  CU(cudaMalloc(&c->bufP, small * esz * frames));
+  CU(cudaMalloc(&c->bufE1, small * esz * frames));
+  CU(cudaMalloc(&c->bufE2, small * esz * frames));
+  CU(cudaMalloc(&c->idx1, small * frames));
+  CU(cudaMalloc(&c->idx2, small * frames));
+  c->scratch_frames = frames;
+  c->scratch_esz = esz;
+  return BC_OK;
+}
+
+// ------------------------------------------------------------------ layer schedule
+Taps taps_for(int kh, int kw, int dil) {
+  Taps t{};
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) {
+      t.dy[ky * kw + kx] = (int8_t)((ky - kh / 2) * dil);
+      t.dx[ky * kw + kx] = (int8_t)((kx - kw / 2) * dil);
+    }
+  return t;
+}
+
+// n frames; x points at this chunk's input; exactly one of logits / labels is non-null.
+template <typename T>
+int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint8_t* labels,
+                  const Lut256* lut, cudaStream_t s) {
+  T* X = (T*)c->bufX;
+  T* Y = (T*)c->bufY;
+  T* P = (T*)c->bufP;
+  T* E1 = (T*)c->bufE1;
+  T* E2 = (T*)c->bufE2;
+  const double esz = sizeof(T);
+  const double in_px_bytes = kind == BC_IN_BGR_U8 ? 3.0 : kind == BC_IN_NCHW_F32 ? 12.0 : 24.0;
+  L(c, "initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
+    launch_initial<T>(x, kind, n, X, c->d_init_w, c->d_init_g, c->d_init_b, c->d_init_a, c->d_lut32, s);
+  });
+  int H = 128, W = 256;   // resolution of X
+  const Taps t1 = taps_for(1, 1, 1);
+  // conv launch with its algorithmic traffic: input + output (+ residual) activations
+  auto conv = [&](const char* name, const T* in, T* out, const T* res, int res_ch, const ConvP& p,
+                  const float* alpha_out, const Taps& taps) {
+    double px = (double)n * H * W;
+    L(c, name, px * (p.cin + p.cout + (res ? res_ch : 0)) * esz, 2.0 * px * p.cin * p.cout * p.ntaps, s,
+      [&] { launch_conv<T>(in, out, res, res_ch, p, alpha_out, n, H, W, taps, s); });
+  };
+  for (const Bottleneck& b : c->blocks) {
+    if (b.kind == 0) {
+      H /= 2; W /= 2;
+      uint8_t* idx = b.cin == 16 ? c->idx1 : c->idx2;
+      double px = (double)n * H * W;
+      L(c, "down_pool_conv2x2", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + b.ci * esz), 2.0 * px * 4 * b.cin * b.ci, s,
+        [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, s); });
+      conv("down_conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, 1));
+      conv("down_expand_add", E2, Y, P, b.cin, b.c3, b.alpha_out, t1);
+      std::swap(X, Y);
+    } else if (b.kind == 1 || b.kind == 2) {
+      bool done = false;
+      if (c->tensor_cores && c->precision == BC_PREC_BF16 && umma_supported(b)) {
+        if constexpr (std::is_same<T, bf16>::value) {
+          double px = (double)n * H * W;
+          double macs = px * (2.0 * b.cin * b.ci + (double)b.ci * b.ci * (b.kind == 1 ? 9 : 10));
+          L(c, b.cin == 64 ? "umma_bottleneck64" : (b.kind == 2 ? "umma_bottleneck128_asym" : "umma_bottleneck128"),
+            px * 2.0 * b.cin * esz, 2.0 * macs, s,
+            [&] { launch_umma_bottleneck((const bf16*)X, (bf16*)Y, b, n, H, W, c->num_sms, s); });
+          done = true;
+        }
+      }
+      if (!done) {
+        conv("proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
+        if (b.kind == 1) {
+          conv(b.dilation > 1 ? "conv3x3_dilated" : "conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, b.dilation));
+          conv("expand1x1_add", E2, Y, X, b.cin, b.c3, b.alpha_out, t1);
+        } else {
+          conv("conv5x1", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(5, 1, 1));
+          conv("conv1x5", E2, E1, nullptr, 0, b.c2b, nullptr, taps_for(1, 5, 1));
+          conv("expand1x1_add", E1, Y, X, b.cin, b.c3, b.alpha_out, t1);
+        }
+      }
+      std::swap(X, Y);
+    } else {
+      const uint8_t* idx = b.cout == 16 ? c->idx1 : c->idx2;   // upsample5_0 pairs with downsample1_0
+      conv("up_proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
+      double px = (double)n * H * W;
+      L(c, "up_unpool_tconv_expand", px * ((b.cin + b.ci) * esz + b.cout + 4.0 * b.cout * esz),
+        2.0 * px * ((double)b.cin * b.cout + 4.0 * b.ci * b.ci + 4.0 * b.ci * b.cout), s,
+        [&] { launch_up_b<T>(X, E1, idx, Y, b, n, H, W, s); });
+      H *= 2; W *= 2;
+      std::swap(X, Y);
+    }
+  }
+  L(c, labels ? "head_tconv_argmax_lut" : "head_tconv_logits",
+    n * (32768.0 * 16 * esz + (labels ? 131072.0 : 131072.0 * 4 * c->num_classes)), n * 2.0 * 32768 * 9 * 16 * c->num_classes, s,
+    [&] { launch_fullconv<T>(X, n, c->num_classes, c->d_full_w, logits, labels, lut, s); });
+  return BC_OK;
+}
+
+size_t input_frame_bytes(int kind) {
+  const size_t px = (size_t)BC_NET_H * BC_NET_W * 3;
+  return kind == BC_IN_BGR_U8 ? px : kind == BC_IN_NCHW_F32 ? px * 4 : px * 8;
+}
+
+int forward(bc_ctx* c, const void* x, int kind, int B, float* logits, uint8_t* labels, const Lut256* lut,
+            cudaStream_t s) {
+  if (!c->net_loaded) return fail(c, BC_ERR_STATE, "bc_load_enet has not been called");
+  if (B < 1 || B > c->max_batch) return fail(c, BC_ERR_ARG, "batch size outside [1, max_batch]");
+  if (kind < 0 || kind > 2) return fail(c, BC_ERR_ARG, "unknown input kind");
+  if (!x) return fail(c, BC_ERR_ARG, "null input pointer");
+  int r;
+  if ((r = ensure_scratch(c))) return r;
+  const int ch = c->scratch_frames;
+  const size_t fb = input_frame_bytes(kind);
+  const size_t px = (size_t)BC_NET_H * BC_NET_W;
+  for (int f0 = 0; f0 < B; f0 += ch) {
+    int n = std::min(ch, B - f0);
+    const void* xi = (const uint8_t*)x + fb * f0;
+    float* lo = logits ? logits + (size_t)f0 * c->num_classes * px : nullptr;
+    uint8_t* la = labels ? labels + (size_t)f0 * px : nullptr;
+    if (c->precision == BC_PREC_BF16) r = forward_chunk<bf16>(c, xi, kind, n, lo, la, lut, s);
+    else r = forward_chunk<float>(c, xi, kind, n, lo, la, lut, s);
+    if (r) return r;
+  }
+  return check_launch(c, "ENet forward");
+}
+
+// ---------------------------------------------------------------------- resize tables
+// cv::resize INTER_LINEAR, 8-bit: per-axis tap pair + 11-bit coefficients (resize.cpp;
+// oracle/cv_ops.py _linear_axis_tables).  x zeroes the fraction at the ends, y only clamps.
+void axis_table(int dst_n, int src_n, bool clamp_frac, int* s0, int* s1, int* c0, int* c1) {
+  double scale = (double)src_n / (double)dst_n;
+  for (int d = 0; d < dst_n; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)std::floor(f);
+    f -= (float)s;
+    int a, b;
+    if (clamp_frac) {
+      if (s < 0) { f = 0.f; s = 0; }
+      if (s >= src_n - 1) { f = 0.f; s = src_n - 1; }
+      a = s; b = std::min(s + 1, src_n - 1);
+    } else {
+      a = std::min(std::max(s, 0), src_n - 1);
+      b = std::min(std::max(s + 1, 0), src_n - 1);
+    }
+    s0[d] = a; s1[d] = b;
+    c0[d] = (int)std::nearbyint((1.f - f) * 2048.f);
+    c1[d] = (int)std::nearbyint(f * 2048.f);
+  }
+}
+
+int get_resize_tab(bc_ctx* c, int h, int w, const ResizeTab** out) {
+  auto key = std::make_pair(h, w);
+  auto it = c->resize_tabs.find(key);
+  if (it != c->resize_tabs.end()) { *out = &it->second; return BC_OK; }
+  ResizeTab t;
+  t.src_h = h; t.src_w = w;
+  if (h == BC_NET_H && w == BC_NET_W) t.mode = 0;
+  else if (h == 2 * BC_NET_H && w == 2 * BC_NET_W) t.mode = 1;
+  else {
+    t.mode = 2;
+    std::vector<int> host(4 * BC_NET_W + 4 * BC_NET_H);
+    int* x0 = host.data(); int* x1 = x0 + BC_NET_W; int* a0 = x1 + BC_NET_W; int* a1 = a0 + BC_NET_W;
+    int* y0 = a1 + BC_NET_W; int* y1 = y0 + BC_NET_H; int* b0 = y1 + BC_NET_H; int* b1 = b0 + BC_NET_H;
+    axis_table(BC_NET_W, w, true, x0, x1, a0, a1);
+    axis_table(BC_NET_H, h, false, y0, y1, b0, b1);
+    CU(cudaMalloc(&t.blob, host.size() * sizeof(int)));
+    CU(cudaMemcpy(t.blob, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice));
+    int* d = (int*)t.blob;
+    t.x0 = d; t.x1 = d + BC_NET_W; t.a0 = d + 2 * BC_NET_W; t.a1 = d + 3 * BC_NET_W;
+    d += 4 * BC_NET_W;
+    t.y0 = d; t.y1 = d + BC_NET_H; t.b0 = d + 2 * BC_NET_H; t.b1 = d + 3 * BC_NET_H;
+  }
+  auto ins = c->resize_tabs.emplace(key, t);
+  *out = &ins.first->second;
+  return BC_OK;
+}
+
+// ------------------------------------------------------------------------ BEV geometry
+// cv::invert for 3x3 (closed form, adjugate * 1/det); oracle/cv_ops.py invert3x3
+void invert3x3(const double* a, double* t) {
+  double d = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+  if (d == 0.0) { for (int i = 0; i < 9; ++i) t[i] = 0.0; return; }
+  d = 1.0 / d;
+  t[0] = (a[4] * a[8] - a[5] * a[7]) * d;
+  t[1] = (a[2] * a[7] - a[1] * a[8]) * d;
+  t[2] = (a[1] * a[5] - a[2] * a[4]) * d;
+  t[3] = (a[5] * a[6] - a[3] * a[8]) * d;
+  t[4] = (a[0] * a[8] - a[2] * a[6]) * d;
+  t[5] = (a[2] * a[3] - a[0] * a[5]) * d;
+  t[6] = (a[3] * a[7] - a[4] * a[6]) * d;
+  t[7] = (a[1] * a[6] - a[0] * a[7]) * d;
+  t[8] = (a[0] * a[4] - a[1] * a[3]) * d;
+}
+
+// bev.py:172-176, 183-190 (float -> int() truncations; Python float == C double)
+int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int ros, BevGeom& g) {
+  if (!c->bev_set) return fail(c, BC_ERR_STATE, "bc_set_bev has not been called");
+  if (!(cell_m > 0.0) || !(w_m > 0.0) || !(h_m > 0.0)) return fail(c, BC_ERR_ARG, "grid extents and cell size must be positive");
+  double cell_px = cell_m * 100 / c->cm_per_px;
+  int Wc = (int)(w_m / cell_m);
+  int occ_w_px = (int)(Wc * cell_px);
+  int Hc = (int)(h_m / cell_m);
+  int occ_h_px = (int)(Hc * cell_px);
+  if (Wc < 1 || Hc < 1 || occ_w_px < 1 || occ_h_px < 1) return fail(c, BC_ERR_ARG, "empty occupancy grid");
+  int left_x = (int)((c->warp_w - occ_w_px) / 2.0);
+  int top_y = c->warp_h - occ_h_px;
+  memcpy(g.Mi, c->Mi, sizeof g.Mi);
+  int bh0 = std::min(16, c->warp_h);
+  g.bw0 = std::min(1024 / bh0, c->warp_w);
+  g.in_rows = c->in_rows; g.in_cols = c->in_cols;
+  g.warp_w = c->warp_w; g.warp_h = c->warp_h;
+  g.occ_w_px = occ_w_px; g.occ_h_px = occ_h_px;
+  g.wl = std::max(left_x, 0); g.wt = std::max(top_y, 0);
+  g.gl = std::max(-left_x, 0); g.gt = std::max(-top_y, 0);
+  g.crop_w = std::max(std::min(g.wl + occ_w_px, c->warp_w) - g.wl, 0);
+  g.crop_h = std::max(c->warp_h - g.wt, 0);
+  g.Wc = Wc; g.Hc = Hc;
+  g.binary = binary ? 1 : 0; g.ros_layout = ros ? 1 : 0;
+  // cv::resize INTER_NEAREST: sx = min(floor(dx * (1 / (dst / src))), src - 1) in fp64
+  g.ifx = 1.0 / ((double)Wc / (double)occ_w_px);
+  g.ify = 1.0 / ((double)Hc / (double)occ_h_px);
+  return BC_OK;
+}
+
+int8_t* grid_dest(bc_ctx* c, int8_t* d_grids, int B, const BevGeom& g) {
+  if (d_grids) return d_grids;
+  if (!c->gather_base) return nullptr;
+  return c->gather_base + (size_t)c->rank * B * g.Hc * g.Wc;
+}
+
+Lut256 make_lut(const uint8_t* h_lut) {
+  Lut256 l;
+  memcpy(l.v, h_lut, 256);
+  return l;
+}
+
+int do_pipeline(bc_ctx* c, const uint8_t* d_bgr, int h, int w, int B, const uint8_t* h_lut, const BevGeom& g,
+                uint8_t* d_labels_out, int8_t* d_grids, cudaStream_t s) {
+  int r;
+  const ResizeTab* rt;
+  if ((r = get_resize_tab(c, h, w, &rt))) return r;
+  const uint8_t* frames = d_bgr;
+  if (rt->mode != 0) {
+    L(c, "resize", (double)B * (3.0 * h * w + 393216.0), 0, s, [&] { launch_resize(d_bgr, h, w, B, c->d_resized, *rt, s); });
+    frames = c->d_resized;
+  }
+  uint8_t* labels = d_labels_out ? d_labels_out : c->d_labels;
+  Lut256 lut = make_lut(h_lut);
+  if ((r = forward(c, frames, BC_IN_BGR_U8, B, nullptr, labels, &lut, s))) return r;
+  L(c, "occgrid", (double)B * ((double)g.in_rows * g.in_cols + (double)g.Hc * g.Wc), 0, s,
+    [&] { launch_occgrid(labels, B, g, d_grids, s); });
+  return check_launch(c, "pipeline");
+}
+
+// The device part of the path (resize .. occupancy grid) replayed as ONE CUDA graph per
+// distinct argument set: a per-frame driver loop then costs a single launch (batch 1 is
+// launch-bound otherwise: ~75 kernels of a few microseconds each).
+int run_pipeline(bc_ctx* c, const uint8_t* d_bgr, int h, int w, int B, const uint8_t* h_lut, double w_m, double h_m,
+                 double cell_m, const BevGeom& g, uint8_t* d_labels_out, int8_t* d_grids, cudaStream_t s) {
+  int r;
+  const ResizeTab* rt;
+  if ((r = get_resize_tab(c, h, w, &rt))) return r;   // may allocate: keep it out of capture
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (s) cudaStreamIsCapturing(s, &st);
+  if (!c->use_graphs || c->profiling || st != cudaStreamCaptureStatusNone)
+    return do_pipeline(c, d_bgr, h, w, B, h_lut, g, d_labels_out, d_grids, s);
+  GraphKey key;
+  memset(&key, 0, sizeof key);
+  key.in = d_bgr; key.out = d_grids; key.labels = d_labels_out;
+  key.h = h; key.w = w; key.B = B; key.binary = g.binary; key.ros = g.ros_layout;
+  key.w_m = w_m; key.h_m = h_m; key.cell_m = cell_m;
+  memcpy(key.lut, h_lut, 256);
+  GraphEntry* ge = nullptr;
+  for (auto& e : c->graphs) if (e.key == key) { ge = &e; break; }
+  if (!ge) {
+    cudaStream_t cs;
+    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    long long l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      r = do_pipeline(c, d_bgr, h, w, B, h_lut, g, d_labels_out, d_grids, cs);
+      e = cudaStreamEndCapture(cs, &graph);
+    }
+    long long nl = c->launches - l0;
+    c->launches = l0;
+    cudaStreamDestroy(cs);
+    if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    if (c->graphs.size() >= 16) { cudaGraphExecDestroy(c->graphs.front().exec); c->graphs.erase(c->graphs.begin()); }
+    GraphEntry ne;
+    ne.key = key; ne.exec = exec; ne.launches = nl;
+    c->graphs.push_back(ne);
+    ge = &c->graphs.back();
+  }
+  CU(cudaGraphLaunch(ge->exec, s));
+  c->launches += ge->launches;
+  return BC_OK;
+}
+
+}  // namespace
+
+// =============================================================================== ABI
+extern "C" {
+
+int bc_abi_version(void) { return 1; }
+
+const char* bc_last_error(const bc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int bc_create(bc_ctx** out, int device, int max_batch) {
+  bc_ctx* c = nullptr;
+  if (!out) return fail(c, BC_ERR_ARG, "null output pointer");
+  *out = nullptr;
+  if (max_batch < 1 || max_batch > 65536) return fail(c, BC_ERR_ARG, "max_batch must be in [1, 65536]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(c, BC_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                    " (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(c, BC_ERR_ARG, "device index out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(c, BC_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(c, BC_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 (Blackwell B200); this library carries sm_100a code only");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(c, BC_ERR_CUDA, cudaGetErrorString(e));
+  std::unique_ptr<bc_ctx> ctx(new bc_ctx());
+  c = ctx.get();
+  c->device = device;
+  c->max_batch = max_batch;
+  c->num_sms = prop.multiProcessorCount;
+  // normalisation LUT, fp64 exactly as numpy evaluates (rgb / 256.0 - mean) / std (models.py:91)
+  const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18
+  std::vector<double> l64(768);
+  std::vector<float> l32(768);
+  for (int u = 0; u < 256; ++u)
+    for (int ch = 0; ch < 3; ++ch) {
+      l64[u * 3 + ch] = ((double)u / 256.0 - mean[ch]) / sd[ch];
+      l32[u * 3 + ch] = (float)l64[u * 3 + ch];   // TensorFlow's fp64 -> fp32 feed cast
+    }
+  CU(cudaMalloc(&c->d_lut64, 768 * sizeof(double)));
+  CU(cudaMalloc(&c->d_lut32, 768 * sizeof(float)));
+  CU(cudaMemcpy(c->d_lut64, l64.data(), 768 * sizeof(double), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_lut32, l32.data(), 768 * sizeof(float), cudaMemcpyHostToDevice));
+  const size_t px = (size_t)BC_NET_H * BC_NET_W;
+  CU(cudaMalloc(&c->d_labels, px * max_batch));
+  CU(cudaMalloc(&c->d_resized, px * 3 * max_batch));
+  *out = ctx.release();
+  return BC_OK;
+}
+
+void bc_destroy(bc_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  invalidate_graphs(c);
+  free_net(c);
+  free_scratch(c);
+  for (auto& kv : c->resize_tabs) if (kv.second.blob) cudaFree(kv.second.blob);
+  for (auto& r : c->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out};
+  for (void* p : ps) if (p) cudaFree(p);
+  delete c;
+}
+
+int bc_load_enet(bc_ctx* c, const void* h_blob, size_t n_bytes) {
+  if (!c) return BC_ERR_ARG;
+  if (!h_blob) return fail(c, BC_ERR_ARG, "null weight blob");
+  CU(cudaSetDevice(c->device));
+  Container ct;
+  int r;
+  c->net_loaded = false;
+  if ((r = parse_container(c, h_blob, n_bytes, ct))) return r;
+  if ((r = build_host_net(c, ct))) return r;
+  if ((r = upload_net(c))) return r;
+  c->net_loaded = true;
+  return BC_OK;
+}
+
+int bc_num_classes(const bc_ctx* c) { return (c && c->net_loaded) ? c->num_classes : BC_ERR_STATE; }
+
+int bc_set_precision(bc_ctx* c, int precision) {
+  if (!c) return BC_ERR_ARG;
+  if (precision != BC_PREC_BF16 && precision != BC_PREC_FP32) return fail(c, BC_ERR_ARG, "unknown precision");
+  if (precision == c->precision) return BC_OK;
+  c->precision = precision;
+  if (c->net_loaded) {
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    return upload_net(c);
+  }
+  return BC_OK;
+}
+
+int bc_set_chunk(bc_ctx* c, int frames) {
+  if (!c) return BC_ERR_ARG;
+  if (frames < 0) return fail(c, BC_ERR_ARG, "chunk must be >= 0");
+  if (frames != c->chunk) { CU(cudaDeviceSynchronize()); invalidate_graphs(c); }
+  c->chunk = frames;
+  return BC_OK;
+}
+
+int bc_set_tensor_cores(bc_ctx* c, int enable) {
+  if (!c) return BC_ERR_ARG;
+  if ((enable != 0) != (c->tensor_cores != 0)) { CU(cudaDeviceSynchronize()); invalidate_graphs(c); }
+  c->tensor_cores = enable ? 1 : 0;
+  return BC_OK;
+}
+
+int bc_set_graphs(bc_ctx* c, int enable) {
+  if (!c) return BC_ERR_ARG;
+  c->use_graphs = enable ? 1 : 0;
+  return BC_OK;
+}
+
+int bc_set_bev(bc_ctx* c, const double h_M[9], int in_rows, int in_cols, int warp_w, int warp_h, double cm_per_px) {
+  if (!c) return BC_ERR_ARG;
+  if (!h_M) return fail(c, BC_ERR_ARG, "null matrix");
+  if (in_rows < 1 || in_cols < 1 || in_rows > 32767 || in_cols > 32767) return fail(c, BC_ERR_ARG, "label-map size out of range");
+  if (warp_w < 1 || warp_h < 1 || warp_w > 32767 || warp_h > 32767) return fail(c, BC_ERR_ARG, "warped size out of range");
+  if (!(cm_per_px > 0.0)) return fail(c, BC_ERR_ARG, "cm_per_px must be positive");
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  invalidate_graphs(c);
+  memcpy(c->M, h_M, sizeof c->M);
+  invert3x3(c->M, c->Mi);
+  c->in_rows = in_rows; c->in_cols = in_cols;
+  c->warp_w = warp_w; c->warp_h = warp_h;
+  c->cm_per_px = cm_per_px;
+  c->bev_set = true;
+  return BC_OK;
+}
+
+int bc_resize_bgr(bc_ctx* c, const uint8_t* d_src, int h, int w, int B, uint8_t* d_dst, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_src || !d_dst) return fail(c, BC_ERR_ARG, "null pointer");
+  if (h < 1 || w < 1 || h > 16384 || w > 16384 || B < 1) return fail(c, BC_ERR_ARG, "bad frame shape");
+  CU(cudaSetDevice(c->device));
+  const ResizeTab* rt;
+  int r;
+  if ((r = get_resize_tab(c, h, w, &rt))) return r;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rt->mode != 0)
+    L(c, "resize", (double)B * (3.0 * h * w + 393216.0), 0, s, [&] { launch_resize(d_src, h, w, B, d_dst, *rt, s); });
+  else launch_resize(d_src, h, w, B, d_dst, *rt, s);   // same size: a device-to-device copy, no kernel
+  return check_launch(c, "resize");
+}
+
+int bc_preprocess(bc_ctx* c, const uint8_t* d_bgr, int h, int w, int B, void* d_out, int out_f64, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_bgr || !d_out) return fail(c, BC_ERR_ARG, "null pointer");
+  if (h < 1 || w < 1 || h > 16384 || w > 16384) return fail(c, BC_ERR_ARG, "bad frame shape");
+  if (B < 1 || B > c->max_batch) return fail(c, BC_ERR_ARG, "batch size outside [1, max_batch]");
+  CU(cudaSetDevice(c->device));
+  const ResizeTab* rt;
+  int r;
+  if ((r = get_resize_tab(c, h, w, &rt))) return r;
+  const uint8_t* src = d_bgr;
+  if (rt->mode != 0) {
+    L(c, "resize", (double)B * (3.0 * h * w + 393216.0), 0, (cudaStream_t)stream,
+      [&] { launch_resize(d_bgr, h, w, B, c->d_resized, *rt, (cudaStream_t)stream); });
+    src = c->d_resized;
+  }
+  L(c, "preprocess", (double)B * 393216.0 * (1 + (out_f64 ? 8 : 4)), 0, (cudaStream_t)stream,
+    [&] { launch_preprocess(src, B, d_out, out_f64, c->d_lut64, (cudaStream_t)stream); });
+  return check_launch(c, "preprocess");
+}
+
+int bc_enet_logits(bc_ctx* c, const void* d_x, int kind, int B, float* d_logits, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_logits) return fail(c, BC_ERR_ARG, "null logits pointer");
+  CU(cudaSetDevice(c->device));
+  return forward(c, d_x, kind, B, d_logits, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int bc_enet_labels(bc_ctx* c, const void* d_x, int kind, int B, const uint8_t h_lut[256], uint8_t* d_labels, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_labels || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
+  CU(cudaSetDevice(c->device));
+  Lut256 lut = make_lut(h_lut);
+  return forward(c, d_x, kind, B, nullptr, d_labels, &lut, (cudaStream_t)stream);
+}
+
+int bc_argmax_lut(bc_ctx* c, const float* d_logits, int B, int C, int H, int W, const uint8_t h_lut[256],
+                  uint8_t* d_labels, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_logits || !d_labels || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
+  if (B < 1 || C < 1 || C > 256 || H < 1 || W < 1) return fail(c, BC_ERR_ARG, "bad logits shape");
+  if ((long long)B * H * W > 0x7fffffffLL) return fail(c, BC_ERR_ARG, "too many pixels");
+  CU(cudaSetDevice(c->device));
+  L(c, "argmax_lut", (double)B * H * W * (4.0 * C + 1), 0, (cudaStream_t)stream,
+    [&] { launch_argmax_lut(d_logits, B, C, H, W, make_lut(h_lut), d_labels, (cudaStream_t)stream); });
+  return check_launch(c, "argmax_lut");
+}
+
+int bc_occgrid_shape(bc_ctx* c, double w_m, double h_m, double cell_m, int* Hc, int* Wc) {
+  if (!c) return BC_ERR_ARG;
+  BevGeom g;
+  int r = make_geom(c, w_m, h_m, cell_m, 0, 0, g);
+  if (r) return r;
+  if (Hc) *Hc = g.Hc;
+  if (Wc) *Wc = g.Wc;
+  return BC_OK;
+}
+
+int bc_occgrid(bc_ctx* c, const uint8_t* d_labels, int B, double w_m, double h_m, double cell_m, int binary,
+               int ros_layout, int8_t* d_grids, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_labels) return fail(c, BC_ERR_ARG, "null labels pointer");
+  if (B < 1 || B > 65535) return fail(c, BC_ERR_ARG, "batch size outside [1, 65535]");
+  BevGeom g;
+  int r = make_geom(c, w_m, h_m, cell_m, binary, ros_layout, g);
+  if (r) return r;
+  int8_t* dst = grid_dest(c, d_grids, B, g);
+  if (!dst) return fail(c, BC_ERR_ARG, "null grid pointer and no gather buffer set");
+  CU(cudaSetDevice(c->device));
+  L(c, "occgrid", (double)B * ((double)g.in_rows * g.in_cols + (double)g.Hc * g.Wc), 0, (cudaStream_t)stream,
+    [&] { launch_occgrid(d_labels, B, g, dst, (cudaStream_t)stream); });
+  return check_launch(c, "occgrid");
+}
+
+int bc_pipeline(bc_ctx* c, const uint8_t* d_bgr, int h, int w, int B, const uint8_t h_lut[256], double w_m,
+                double h_m, double cell_m, int binary, int ros_layout, uint8_t* d_labels_out, int8_t* d_grids,
+                void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_bgr || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
+  if (h < 1 || w < 1 || h > 16384 || w > 16384) return fail(c, BC_ERR_ARG, "bad frame shape");
+  if (B < 1 || B > c->max_batch) return fail(c, BC_ERR_ARG, "batch size outside [1, max_batch]");
+  if (!c->net_loaded) return fail(c, BC_ERR_STATE, "bc_load_enet has not been called");
+  BevGeom g;
+  int r = make_geom(c, w_m, h_m, cell_m, binary, ros_layout, g);
+  if (r) return r;
+  if (c->in_rows != BC_NET_H || c->in_cols != BC_NET_W)
+    return fail(c, BC_ERR_ARG, "calibration input size must be (256, 512) for the ENet pipeline (bev.py:169)");
+  int8_t* dst = grid_dest(c, d_grids, B, g);
+  if (!dst) return fail(c, BC_ERR_ARG, "null grid pointer and no gather buffer set");
+  CU(cudaSetDevice(c->device));
+  int r2;
+  if ((r2 = ensure_scratch(c))) return r2;
+  return run_pipeline(c, d_bgr, h, w, B, h_lut, w_m, h_m, cell_m, g, d_labels_out, dst, (cudaStream_t)stream);
+}
+
+int bc_pipeline_host(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const uint8_t h_lut[256], double w_m,
+                     double h_m, double cell_m, int binary, int ros_layout, int8_t* h_grids, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!h_bgr || !h_grids || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
+  if (h < 1 || w < 1 || h > 16384 || w > 16384) return fail(c, BC_ERR_ARG, "bad frame shape");
+  if (B < 1 || B > c->max_batch) return fail(c, BC_ERR_ARG, "batch size outside [1, max_batch]");
+  if (!c->net_loaded) return fail(c, BC_ERR_STATE, "bc_load_enet has not been called");
+  BevGeom g;
+  int r = make_geom(c, w_m, h_m, cell_m, binary, ros_layout, g);
+  if (r) return r;
+  if (c->in_rows != BC_NET_H || c->in_cols != BC_NET_W)
+    return fail(c, BC_ERR_ARG, "calibration input size must be (256, 512) for the ENet pipeline (bev.py:169)");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t in_bytes = (size_t)B * h * w * 3;
+  size_t out_bytes = (size_t)B * g.Hc * g.Wc;
+  if (c->frames_in_bytes < in_bytes) {
+    CU(cudaStreamSynchronize(s));
+    invalidate_graphs(c);
+    if (c->d_frames_in) cudaFree(c->d_frames_in);
+    c->d_frames_in = nullptr; c->frames_in_bytes = 0;
+    CU(cudaMalloc(&c->d_frames_in, in_bytes));
+    c->frames_in_bytes = in_bytes;
+  }
+  if (c->grids_out_bytes < out_bytes) {
+    CU(cudaStreamSynchronize(s));
+    invalidate_graphs(c);
+    if (c->d_grids_out) cudaFree(c->d_grids_out);
+    c->d_grids_out = nullptr; c->grids_out_bytes = 0;
+    CU(cudaMalloc(&c->d_grids_out, out_bytes));
+    c->grids_out_bytes = out_bytes;
+  }
+  if ((r = ensure_scratch(c))) return r;
+  const ResizeTab* rt;
+  if ((r = get_resize_tab(c, h, w, &rt))) return r;   // may allocate: keep it out of capture
+
+  CU(cudaMemcpyAsync(c->d_frames_in, h_bgr, in_bytes, cudaMemcpyHostToDevice, s));
+  if ((r = run_pipeline(c, c->d_frames_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, c->d_grids_out, s))) return r;
+  CU(cudaMemcpyAsync(h_grids, c->d_grids_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return BC_OK;
+}
+
+int bc_gather_setup(bc_ctx* c, void* d_gather_base, int rank, int world) {
+  if (!c) return BC_ERR_ARG;
+  if (d_gather_base && (world < 1 || rank < 0 || rank >= world)) return fail(c, BC_ERR_ARG, "rank outside [0, world)");
+  c->gather_base = (int8_t*)d_gather_base;
+  c->rank = d_gather_base ? rank : 0;
+  c->world = d_gather_base ? world : 1;
+  return BC_OK;
+}
+
+long long bc_launch_count(const bc_ctx* c) { return c ? c->launches : 0; }
+
+int bc_set_profile(bc_ctx* c, int enable) {
+  if (!c) return BC_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  for (auto& r : c->prof) { c->ev_pool.push_back(r.start); c->ev_pool.push_back(r.stop); }
+  c->prof.clear();
+  c->profiling = enable ? 1 : 0;
+  return BC_OK;
+}
+
+const char* bc_profile_json(bc_ctx* c) {
+  if (!c) return "[]";
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  struct Agg { long long n = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) != cudaSuccess) continue;
+    Agg& a = agg[r.name];
+    a.n++; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+  }
+  std::string out = "[";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"launches\": %lld, \"ms\": %.6f, \"bytes\": %.0f, \"flops\": %.0f}",
+             first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+    out += buf;
+    first = false;
+  }
+  out += "]";
+  c->prof_json = out;
+  return c->prof_json.c_str();
+}
+
+}  // extern "C"

@@ -57,6 +57,7 @@ struct BevGeom {            // kernel parameter block for K9 (passed by value)
   int crop_w, crop_h;
   int Wc, Hc;               // grid cells
   int binary, ros_layout;
+  double ifx, ify;          // nearest-resize source step (cv::resize INTER_NEAREST, fp64)
 };
 
 // ------------------------------------------------------------------ launchers (enet_simt.cu)
@@ -101,7 +102,6 @@ void launch_preprocess(const uint8_t* bgr256, int B, void* out, int out_f64, con
                        cudaStream_t s);
 void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lut256& lut,
                        uint8_t* labels, cudaStream_t s);
-void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, const int* xi, const int* yi,
-                    int8_t* grids, cudaStream_t s);
+void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s);
 
 }  // namespace bc

@@ -168,19 +168,20 @@ __device__ __forceinline__ bool is_occ(int v, int binary) {
   return binary ? (v == 1) : (v == 1 || v == 3);   // bev.py:128 / bev.py:196
 }
 
-// One thread per grid cell.  The cell takes template pixel (yi[cy], xi[cx]) (nearest
+// One thread per grid cell.  The cell takes template pixel (ty, tx) (nearest
 // resize); if that pixel is "occupied" the 3x3 opening decides whether it is a speck:
 //   opened(p) = OR_{q in N3(p)} AND_{r in N3(q)} occ(r)   (erode ignores pixels outside
 //   the template, dilate treats them as 0 -- OpenCV default border values)
 __global__ void __launch_bounds__(128)
-k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, const int* __restrict__ xi,
-          const int* __restrict__ yi, int8_t* __restrict__ grids) {
+k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int8_t* __restrict__ grids) {
   int cx = blockIdx.x * blockDim.x + threadIdx.x;
   int cy = blockIdx.y;
   int n = blockIdx.z;
   if (cx >= g.Wc) return;
   const uint8_t* lab = labels + (size_t)n * g.in_rows * g.in_cols;
-  int tx = xi[cx], ty = yi[cy];
+  // cv::resize INTER_NEAREST (bev.py:209-212): min(floor(d * ifx), src - 1) in fp64
+  int tx = min((int)floor(__dmul_rn((double)cx, g.ifx)), g.occ_w_px - 1);
+  int ty = min((int)floor(__dmul_rn((double)cy, g.ify)), g.occ_h_px - 1);
   int v = template_px(lab, g, tx, ty);
   if (is_occ(v, g.binary)) {
     // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i); outside = "ignore"
@@ -228,10 +229,9 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, const int* __rest
   grids[(size_t)n * cells + o] = (int8_t)out;
 }
 
-void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, const int* xi, const int* yi,
-                    int8_t* grids, cudaStream_t s) {
+void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s) {
   dim3 grid((g.Wc + 127) / 128, g.Hc, B);
-  k_occgrid<<<grid, 128, 0, s>>>(labels, g, xi, yi, grids);
+  k_occgrid<<<grid, 128, 0, s>>>(labels, g, grids);
 }
 
 }  // namespace bc

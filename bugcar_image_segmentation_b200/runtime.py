@@ -1,0 +1,40 @@
+"""Host-side plumbing shared by the drop-in modules: torch for device memory and
+streams, ctypes for the C ABI.  PyTorch is plumbing here, not the product."""
+import os
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_MAX_BATCH = int(os.environ.get("BUGCAR_MAX_BATCH", "256"))
+PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_DIR = os.path.dirname(PACKAGE_DIR)
+SYNTHETIC_WEIGHTS = os.path.join(REPO_DIR, "pretrained_models", "enet_synthetic_seed42.bcw")
+
+
+def torch_cuda(device=None):
+    """import torch and make sure a CUDA device exists (fail loudly otherwise)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bugcar_image_segmentation_b200 needs a B200 GPU: torch.cuda.is_available() is "
+                           "False and there is no CPU fallback")
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if "LOCAL_RANK" in os.environ else torch.cuda.current_device()
+    return torch, int(device)
+
+
+def stream_handle(torch, device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def to_device_u8(torch, device, a):
+    """numpy/torch array -> contiguous uint8 CUDA tensor (no copy when already there)"""
+    if isinstance(a, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).to(f"cuda:{device}", non_blocking=False)
+    if a.dtype != torch.uint8:
+        a = a.to(torch.uint8)
+    return a.to(f"cuda:{device}").contiguous()
+
+
+def new_context(device, max_batch=None):
+    return _lib.Context(device, DEFAULT_MAX_BATCH if max_batch is None else max_batch)

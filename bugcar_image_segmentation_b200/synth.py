@@ -76,3 +76,25 @@ def calibration(name, in_rows=INPUT_H, in_cols=INPUT_W):
     return {"output image size": [ww, wh], "input image size": [in_rows, in_cols],
             "bev matrix": M.reshape(-1).tolist(), "distance to target": [0, 100],
             "tile_length": 60, "cm_per_px": cm, "yaw": 0.0, "is_laserscan": False}
+
+
+# ---- colour-region frames (tools/train_synthetic.py; parity inputs with real class structure)
+PALETTE = np.array([     # 15 BGR colours standing for the class ids of note_label:1-15
+    [128, 64, 128], [255, 255, 255], [232, 35, 244], [70, 70, 70], [156, 102, 102],
+    [153, 153, 190], [30, 170, 250], [0, 220, 220], [153, 153, 153], [35, 142, 107],
+    [180, 130, 70], [60, 20, 220], [142, 0, 0], [100, 60, 0], [32, 11, 119]], np.uint8)
+
+
+def region_frame(seed, h=INPUT_H, w=INPUT_W, n_rect=24):
+    """(bgr uint8 (h,w,3), class map uint8 (h,w)): random rectangles filled with palette
+    colours, +-12 % brightness jitter per rectangle, N(0,8) pixel noise."""
+    rng = np.random.default_rng(seed)
+    lab = np.full((h, w), rng.integers(0, 15), np.uint8)
+    gain = np.ones((h, w), np.float64)
+    for _ in range(n_rect):
+        y0, x0 = int(rng.integers(0, h)), int(rng.integers(0, w))
+        rh, rw = int(rng.integers(h // 8, h // 2)), int(rng.integers(w // 8, w // 2))
+        lab[y0:y0 + rh, x0:x0 + rw] = rng.integers(0, 15)
+        gain[y0:y0 + rh, x0:x0 + rw] = rng.uniform(0.88, 1.12)
+    img = PALETTE[lab].astype(np.float64) * gain[:, :, None] + rng.normal(0.0, 8.0, (h, w, 3))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8), lab

@@ -83,6 +83,9 @@ int bc_set_chunk(bc_ctx* ctx, int frames);
 /* 1 (default): regular bottlenecks run as fused tcgen05 kernels in bf16 mode;
  * 0: every layer runs on the CUDA-core kernels (bring-up / A-B comparison). */
 int bc_set_tensor_cores(bc_ctx* ctx, int enable);
+/* 1 (default): bc_pipeline / bc_pipeline_host replay their kernel chain as one CUDA graph
+ * per distinct argument set (what makes batch 1 sub-millisecond); 0: plain launches. */
+int bc_set_graphs(bc_ctx* ctx, int enable);
 /* Replaces bev_transform_tools.__init__/fromJSON state (bev.py:13-41): src->dst
  * homography `h_M` (row-major 3x3, bev.py:31-32), label-map shape (rows, cols)
  * ("input image size", bev.py:30,169), warped size (ww, wh) ("output image size",
@@ -145,6 +148,13 @@ int bc_gather_setup(bc_ctx* ctx, void* d_gather_base, int rank, int world);
 
 /* number of kernels this context launched since creation (bench.py "gpu_launches") */
 long long bc_launch_count(const bc_ctx* ctx);
+/* Per-kernel timing for the roofline report: while enabled every launch is bracketed by a
+ * CUDA event pair on its stream (CUDA graphs are bypassed); bc_profile_json synchronises
+ * and returns a JSON array [{"kernel", "launches", "ms", "bytes", "flops"}] aggregated by
+ * kernel since the last bc_set_profile call ("bytes"/"flops" are the ALGORITHMIC traffic
+ * and work of those launches).  The string is owned by the context. */
+int bc_set_profile(bc_ctx* ctx, int enable);
+const char* bc_profile_json(bc_ctx* ctx);
 
 #ifdef __cplusplus
 }
