@@ -33,6 +33,7 @@ SIGNATURES = {
     "bc_resize_bgr": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "bc_preprocess": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "bc_enet_logits": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "bc_enet_block_output": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "bc_enet_labels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bc_argmax_lut": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "bc_occgrid_shape": (_i, [_vp, _d, _d, _d, C.POINTER(_i), C.POINTER(_i)]),
@@ -156,6 +157,9 @@ class Context:
 
     def enet_logits(self, d_x, kind, B, d_logits, stream=None):
         self._ck(self.lib.bc_enet_logits(self.h, _ptr(d_x), kind, B, _ptr(d_logits), _ptr(stream)))
+
+    def enet_block_output(self, d_x, kind, B, block, d_out, stream=None):
+        self._ck(self.lib.bc_enet_block_output(self.h, _ptr(d_x), kind, B, int(block), _ptr(d_out), _ptr(stream)))
 
     def enet_labels(self, d_x, kind, B, lut, d_labels, stream=None):
         self._ck(self.lib.bc_enet_labels(self.h, _ptr(d_x), kind, B, _lut(lut), _ptr(d_labels), _ptr(stream)))

@@ -486,7 +486,7 @@ Taps taps_for(int kh, int kw, int dil) {
 // n frames; x points at this chunk's input; exactly one of logits / labels is non-null.
 template <typename T>
 int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint8_t* labels,
-                  const Lut256* lut, cudaStream_t s) {
+                  const Lut256* lut, cudaStream_t s, int stop_after = -2, float* dump = nullptr) {
   T* X = (T*)c->bufX;
   T* Y = (T*)c->bufY;
   T* P = (T*)c->bufP;
@@ -498,6 +498,8 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
     launch_initial<T>(x, kind, n, X, c->d_init_w, c->d_init_g, c->d_init_b, c->d_init_a, c->d_lut32, s);
   });
   int H = 128, W = 256;   // resolution of X
+  if (stop_after == -1) { launch_export_nchw<T>(X, dump, n, 16, H, W, s); return BC_OK; }
+  int block_index = 0;
   const Taps t1 = taps_for(1, 1, 1);
   // conv launch with its algorithmic traffic: input + output (+ residual) activations
   auto conv = [&](const char* name, const T* in, T* out, const T* res, int res_ch, const ConvP& p,
@@ -550,6 +552,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       H *= 2; W *= 2;
       std::swap(X, Y);
     }
+    if (block_index++ == stop_after) { launch_export_nchw<T>(X, dump, n, b.cout, H, W, s); return BC_OK; }
   }
   L(c, labels ? "head_tconv_argmax_lut" : "head_tconv_logits",
     n * (32768.0 * 16 * esz + (labels ? 131072.0 : 131072.0 * 4 * c->num_classes)), n * 2.0 * 32768 * 9 * 16 * c->num_classes, s,
@@ -943,6 +946,22 @@ int bc_enet_labels(bc_ctx* c, const void* d_x, int kind, int B, const uint8_t h_
   CU(cudaSetDevice(c->device));
   Lut256 lut = make_lut(h_lut);
   return forward(c, d_x, kind, B, nullptr, d_labels, &lut, (cudaStream_t)stream);
+}
+
+int bc_enet_block_output(bc_ctx* c, const void* d_x, int kind, int B, int block, float* d_out, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!c->net_loaded) return fail(c, BC_ERR_STATE, "bc_load_enet has not been called");
+  if (!d_x || !d_out) return fail(c, BC_ERR_ARG, "null pointer");
+  if (block < -1 || block >= (int)c->blocks.size()) return fail(c, BC_ERR_ARG, "block index out of range");
+  if (kind < 0 || kind > 2) return fail(c, BC_ERR_ARG, "unknown input kind");
+  CU(cudaSetDevice(c->device));
+  int r;
+  if ((r = ensure_scratch(c))) return r;
+  if (B < 1 || B > c->scratch_frames) return fail(c, BC_ERR_ARG, "batch size outside [1, chunk]");
+  if (c->precision == BC_PREC_BF16) r = forward_chunk<bf16>(c, d_x, kind, B, nullptr, nullptr, nullptr, (cudaStream_t)stream, block, d_out);
+  else r = forward_chunk<float>(c, d_x, kind, B, nullptr, nullptr, nullptr, (cudaStream_t)stream, block, d_out);
+  if (r) return r;
+  return check_launch(c, "block output");
 }
 
 int bc_argmax_lut(bc_ctx* c, const float* d_logits, int B, int C, int H, int W, const uint8_t h_lut[256],

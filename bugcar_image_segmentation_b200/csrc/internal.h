@@ -79,6 +79,9 @@ template <typename T>
 void launch_fullconv(const T* x, int B, int C, const float* w, float* logits, uint8_t* labels,
                      const Lut256* lut, cudaStream_t s);
 
+template <typename T>
+void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cudaStream_t s);
+
 // ------------------------------------------------------------------ launchers (enet_umma.cu)
 // Fused regular bottleneck (1x1 -> 3x3 -> 1x1 + residual) on tcgen05; bf16 only.
 // Returns false when the shape is not covered (caller falls back to CUDA-core kernels).

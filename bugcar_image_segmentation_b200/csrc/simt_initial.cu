@@ -92,4 +92,22 @@ void launch_initial(const void* x, int kind, int B, T* out, const float* w, cons
 template void launch_initial<float>(const void*, int, int, float*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
 template void launch_initial<bf16>(const void*, int, int, bf16*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
 
+// ------------------------------------------------------------- debug / parity export
+// NHWC activation (storage type T) -> fp32 NCHW, for per-block parity tests.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_export_nchw(const T* __restrict__ in, float* __restrict__ out, int C, int HW, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over n*C*HW, NCHW order
+  if (i >= total) return;
+  size_t yx = i % HW, c = (i / HW) % C, n = i / ((size_t)HW * C);
+  out[i] = (float)in[(n * HW + yx) * C + c];
+}
+template <typename T>
+void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  size_t total = (size_t)B * C * H * W;
+  k_export_nchw<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, C, H * W, total);
+}
+template void launch_export_nchw<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template void launch_export_nchw<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
+
 }  // namespace bc

@@ -107,6 +107,11 @@ int bc_preprocess(bc_ctx* ctx, const uint8_t* d_bgr, int h, int w, int B,
 /* sess.run of the frozen graph (models.py:43-44): logits fp32 NCHW (B,C,256,512). */
 int bc_enet_logits(bc_ctx* ctx, const void* d_x, int kind, int B, float* d_logits,
                    void* stream);
+/* Parity/debug: activation after block `block` (-1 = initial block, 0.. = the 27 bottlenecks
+ * in network order) as fp32 NCHW (B,C,H,W); B <= the chunk size.  No reference counterpart:
+ * the frozen graph exposes only its output tensor (models.py:16). */
+int bc_enet_block_output(bc_ctx* ctx, const void* d_x, int kind, int B, int block, float* d_out,
+                         void* stream);
 /* Forward + tf.math.argmax(axis=1) (models.py:55) + class LUT fused in the head.
  * h_lut[class] -> label; the 3-way LUT of models.py:56-58 gives predict, the
  * {0,1}->1 LUT of models.py:79-80 gives predict_binary.  d_labels uint8 (B,256,512). */
