@@ -81,6 +81,7 @@ struct bc_ctx {
   int precision = BC_PREC_BF16;
   int chunk = 0;            // 0 = default
   int tensor_cores = 1;
+  bool umma_ready = false;
   int use_graphs = 1;
 
   // ---- network (host copies, folded, fp32)
@@ -378,6 +379,7 @@ int build_host_net(bc_ctx* c, const Container& ct) {
 
 // ------------------------------------------------------------------- device upload
 void free_net(bc_ctx* c) {
+  for (Bottleneck& b : c->blocks) { umma_free(b.um_a); umma_free(b.um_b); }
   for (void* p : c->dev_allocs) cudaFree(p);
   c->dev_allocs.clear();
   c->blocks.clear();
@@ -437,6 +439,33 @@ int upload_net(bc_ctx* c) {
     if ((r = upload_conv(c, hb.cm, bf, b.cm))) return r;
     if ((r = upload_vec(c, hb.alpha_out, false, &b.alpha_out))) return r;
     c->blocks.push_back(b);
+  }
+  // tcgen05 operand packs (bf16 mode): conv (+ expansion + the NEXT block's projection)
+  c->umma_ready = false;
+  if (bf && umma_available()) {
+    for (size_t i = 0; i < c->blocks.size(); ++i) {
+      Bottleneck& b = c->blocks[i];
+      if (!umma_supported(b)) continue;
+      const HostBlock& hb = c->h_blocks[i];
+      const HostBlock* nx = nullptr;
+      if (i + 1 < c->blocks.size() && umma_supported(c->blocks[i + 1]) && c->blocks[i + 1].cin == b.cin)
+        nx = &c->h_blocks[i + 1];
+      const float* nw = nx ? nx->c1.w.data() : nullptr;
+      const float* nb = nx ? nx->c1.bias.data() : nullptr;
+      const float* na = nx ? nx->c1.alpha.data() : nullptr;
+      bool ok;
+      if (b.kind == 1) {
+        ok = umma_build(b.um_a, b.cin, b.ci, hb.c2.w.data(), 9, hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
+                        hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
+      } else {
+        ok = umma_build(b.um_a, b.cin, b.ci, hb.c2.w.data(), 5, hb.c2.bias.data(), hb.c2.alpha.data(), nullptr, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, nullptr) &&
+             umma_build(b.um_b, b.cin, b.ci, hb.c2b.w.data(), 5, hb.c2b.bias.data(), hb.c2b.alpha.data(), hb.c3.w.data(),
+                        hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
+      }
+      if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
+    }
+    c->umma_ready = true;
   }
   return BC_OK;
 }
@@ -500,6 +529,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
   int H = 128, W = 256;   // resolution of X
   if (stop_after == -1) { launch_export_nchw<T>(X, dump, n, 16, H, W, s); return BC_OK; }
   int block_index = 0;
+  bool e1_ready = false;    // E1 already holds this block's projection (written by the previous tcgen05 kernel)
   const Taps t1 = taps_for(1, 1, 1);
   // conv launch with its algorithmic traffic: input + output (+ residual) activations
   auto conv = [&](const char* name, const T* in, T* out, const T* res, int res_ch, const ConvP& p,
@@ -520,17 +550,35 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       std::swap(X, Y);
     } else if (b.kind == 1 || b.kind == 2) {
       bool done = false;
-      if (c->tensor_cores && c->precision == BC_PREC_BF16 && umma_supported(b)) {
+      if (c->tensor_cores && c->umma_ready && c->precision == BC_PREC_BF16 && umma_supported(b)) {
         if constexpr (std::is_same<T, bf16>::value) {
-          double px = (double)n * H * W;
-          double macs = px * (2.0 * b.cin * b.ci + (double)b.ci * b.ci * (b.kind == 1 ? 9 : 10));
-          L(c, b.cin == 64 ? "umma_bottleneck64" : (b.kind == 2 ? "umma_bottleneck128_asym" : "umma_bottleneck128"),
-            px * 2.0 * b.cin * esz, 2.0 * macs, s,
-            [&] { launch_umma_bottleneck((const bf16*)X, (bf16*)Y, b, n, H, W, c->num_sms, s); });
+          const double px = (double)n * H * W;
+          if (!e1_ready) conv("proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
+          cudaError_t ce = cudaSuccess;
+          const int has_next = (b.kind == 1 ? b.um_a : b.um_b).has_next ? 1 : 0;
+          const double io = px * (2.0 * b.cin + b.ci * (1 + has_next)) * esz;
+          if (b.kind == 1) {
+            L(c, b.cin == 64 ? "umma_bottleneck64" : "umma_bottleneck128", io,
+              2.0 * px * (9.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
+              [&] { ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)X, (bf16*)Y, (bf16*)E2, n, H, W,
+                                     taps_for(3, 3, b.dilation), 0, has_next, c->num_sms, s); });
+            std::swap(E1, E2);        // e1' of the next block was written to E2
+          } else {
+            L(c, "umma_conv5x1", px * 2.0 * b.ci * esz, 2.0 * px * 5.0 * b.ci * b.ci, s,
+              [&] { ce = launch_umma(b.um_a, (const bf16*)E1, nullptr, nullptr, (bf16*)E2, n, H, W, taps_for(5, 1, 1), 1, 0,
+                                     c->num_sms, s); });
+            if (ce == cudaSuccess)
+              L(c, "umma_bottleneck128_asym", io, 2.0 * px * (5.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
+                [&] { ce = launch_umma(b.um_b, (const bf16*)E2, (const bf16*)X, (bf16*)Y, (bf16*)E1, n, H, W,
+                                       taps_for(1, 5, 1), 0, has_next, c->num_sms, s); });
+          }
+          if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 bottleneck launch: ") + cudaGetErrorString(ce));
+          e1_ready = has_next != 0;
           done = true;
         }
       }
       if (!done) {
+        e1_ready = false;
         conv("proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
         if (b.kind == 1) {
           conv(b.dilation > 1 ? "conv3x3_dilated" : "conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, b.dilation));

@@ -23,14 +23,13 @@ struct ConvP {
   int cin = 0, cout = 0, ntaps = 0;
 };
 
-// tcgen05 operand pack for one fused regular bottleneck (bf16, K-major core-matrix
-// layout, see enet_umma.cu)
-struct UmmaP {
-  bf16* w1 = nullptr;   // [CI][C]
-  bf16* w2 = nullptr;   // [taps][CI][CI]
-  bf16* w3 = nullptr;   // [C][CI]
-  void* blob = nullptr; // single device allocation holding the three + params
-  size_t blob_bytes = 0;
+// tcgen05 operand pack of one bottleneck kernel launch (enet_umma.cu): the exact
+// shared-memory image of the K-major swizzled bf16 weights + the fp32 bias / slope block
+struct UmmaPack {
+  uint8_t* wblob = nullptr;
+  float* fparams = nullptr;
+  int C = 0, CI = 0, ntaps = 0;
+  bool has_exp = false, has_next = false;
 };
 
 struct Bottleneck {
@@ -39,7 +38,7 @@ struct Bottleneck {
   int cin, cout, ci, dilation;
   ConvP c1, c2, c2b, c3, cm; // proj / mid / mid-second (asym) / expand / main (up)
   float* alpha_out = nullptr;
-  UmmaP umma;
+  UmmaPack um_a, um_b;       // um_b: second half (1x5 + expansion) of an asymmetric bottleneck
 };
 
 struct Taps { int8_t dy[9]; int8_t dx[9]; };
@@ -83,13 +82,16 @@ template <typename T>
 void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cudaStream_t s);
 
 // ------------------------------------------------------------------ launchers (enet_umma.cu)
-// Fused regular bottleneck (1x1 -> 3x3 -> 1x1 + residual) on tcgen05; bf16 only.
-// Returns false when the shape is not covered (caller falls back to CUDA-core kernels).
-bool umma_supported(const Bottleneck& bn);
-void umma_pack(Bottleneck& bn, const std::vector<float>& w1, const std::vector<float>& w2,
-               const std::vector<float>& w3);   // folded fp32 [tap][cin][cout] inputs
-void launch_umma_bottleneck(const bf16* x, bf16* y, const Bottleneck& bn, int B, int H, int W,
-                            int num_sms, cudaStream_t s);
+// Fused bottleneck on tcgen05 (bf16 only): conv taps on e1 -> [expansion + residual -> y ->
+// next block's projection].  See enet_umma.cu for the data flow.
+bool umma_available();                        // driver exposes cuTensorMapEncodeTiled
+bool umma_supported(const Bottleneck& bn);    // regular / dilated / asymmetric at C = 64 or 128
+bool umma_build(UmmaPack& out, int C, int CI, const float* conv_w, int ntaps, const float* conv_b,
+                const float* conv_a, const float* exp_w, const float* exp_b, const float* exp_a,
+                const float* alpha_out, const float* next_w, const float* next_b, const float* next_a);
+void umma_free(UmmaPack& p);
+cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n,
+                        int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
 
 // ------------------------------------------------------------------ launchers (prepost.cu)
 struct ResizeTab {          // device tables for cv2.resize INTER_LINEAR, one (h,w)
