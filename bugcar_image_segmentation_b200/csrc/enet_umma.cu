@@ -60,6 +60,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1)
@@ -163,10 +169,11 @@ struct UmmaSmem {
   static constexpr int W3_BYTES = C * RB;           // [C out][CI in]
   static constexpr int XSUB = 128 * 128;            // one 64-channel sub-tile of x / y
   static constexpr int NSUB = C / 64;
+  static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
   static constexpr int W1_SUB = CI * 128;           // [CI out][64 in] sub-tile of the next projection
   // offsets (all multiples of 1024)
-  static constexpr int OFF_X = 0;
-  static constexpr int OFF_TAPS = OFF_X + NSUB * XSUB;
+  static constexpr int OFF_X = 0;                   // two x / y tiles (double buffered)
+  static constexpr int OFF_TAPS = OFF_X + 2 * XBUF;
   static constexpr int OFF_E2 = OFF_TAPS + 9 * TAP_BYTES;
   static constexpr int OFF_W = OFF_E2 + TAP_BYTES;                    // weight image starts here
   static constexpr int OFF_W2 = OFF_W;
@@ -176,11 +183,24 @@ struct UmmaSmem {
   static constexpr int OFF_F = OFF_W + ((W_BYTES + 1023) / 1024) * 1024;
   static constexpr int NF = 4 * CI + 3 * C;
   static constexpr int OFF_BAR = OFF_F + ((NF * 4 + 63) / 64) * 64;
-  static constexpr int TOTAL = OFF_BAR + 64;
+  static constexpr int TOTAL = OFF_BAR + 128;
+  // TMEM columns: D1 double buffered
+  static constexpr uint32_t COL_D1 = 0, COL_D2 = 2 * CI, COL_D3 = 2 * CI + C;
+  static constexpr uint32_t TMEM_COLS = (2 * CI + C + CI) <= 128 ? 128 : 256;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warp-specialised persistent kernel, 192 threads:
+//   warp 0    TMA producer   conv taps of tile k+1 as soon as the conv MMAs of tile k retire;
+//                            residual tile x double buffered
+//   warp 1    MMA issuer     conv(k) -> expansion(k) -> conv(k+1) -> projection(k); D1 double buffered
+//   warps 2-5 epilogue       one TMEM lane (= pixel) per thread: D1 -> e2 (smem), D2 + x -> y (smem,
+//                            TMA store), D3 -> e1' (global)
 template <int C, int CI>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(192, 1)
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
@@ -194,163 +214,199 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   float* sf = (float*)(smem + S::OFF_F);
   const float *b2 = sf, *a2 = sf + CI, *b3 = sf + 2 * CI, *a3 = b3 + C, *aout = a3 + C, *b1n = aout + C, *a1n = b1n + CI;
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
-  const uint32_t bar_full = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
-  uint32_t* tmem_slot = (uint32_t*)&bars[2];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  enum { TAP_FULL = 0, TAP_EMPTY, X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D1_EMPTY0, D1_EMPTY1,
+         E2_FULL, D2_FULL, Y_FULL, D3_FULL, W_FULL, NBARS };
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- one-time setup: weights + parameters to smem, barriers, TMEM
-  for (int i = tid; i < S::W_BYTES / 16; i += 128)
-    reinterpret_cast<uint4*>(smem + S::OFF_W)[i] = reinterpret_cast<const uint4*>(p.wblob)[i];
-  for (int i = tid; i < S::NF; i += 128) sf[i] = p.fparams[i];
+  // ---- one-time setup: barriers, weights + parameters to smem (two bulk copies), TMEM
   if (tid == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_mma, 1);
+    const int one[] = {TAP_FULL, TAP_EMPTY, X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D2_FULL, D3_FULL, W_FULL};
+    for (int b : one) mbar_init(bar(b), 1);
+    const int all[] = {D1_EMPTY0, D1_EMPTY1, E2_FULL, Y_FULL};
+    for (int b : all) mbar_init(bar(b), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar(W_FULL), S::W_BYTES + S::NF * 4);
+    bulk_load(sbase + S::OFF_W, p.wblob, S::W_BYTES, bar(W_FULL));
+    bulk_load(sbase + S::OFF_F, p.fparams, S::NF * 4, bar(W_FULL));
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  fence_proxy_async();          // weight image written by the generic proxy, read by tcgen05.mma
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_lane = tmem + ((uint32_t)(warp * 32) << 16);
-  constexpr uint32_t COL_D1 = 0, COL_D2 = 32, COL_D3 = 32 + C;
   constexpr uint32_t IDESC_CONV = instr_desc(128, CI), IDESC_EXP = instr_desc(128, C), IDESC_PROJ = instr_desc(128, CI);
+  const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // my tiles
+  const bool full = !p.conv_only;
 
-  uint32_t ph_full = 0, ph_mma = 0;
-  const int m = tid;            // row of the tile = pixel = TMEM lane
-
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    const int n = tile / p.tiles_per_frame;
-    const int y0 = (tile % p.tiles_per_frame) * p.rows_per_tile;
-    // ---- 1. TMA: the conv taps of e1 and (unless conv_only) the residual tile of x
-    if (tid == 0) {
-      uint32_t bytes = (uint32_t)p.ntaps * S::TAP_BYTES + (p.conv_only ? 0 : S::NSUB * S::XSUB);
-      mbar_expect_tx(bar_full, bytes);
-      for (int t = 0; t < p.ntaps; ++t)
-        tma_load_4d(sbase + S::OFF_TAPS + t * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar_full);
-      if (!p.conv_only)
-        for (int s = 0; s < S::NSUB; ++s) tma_load_2d(sbase + S::OFF_X + s * S::XSUB, &map_x, s * 64, tile * 128, bar_full);
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      for (int k = 0; k < T; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int n = tile / p.tiles_per_frame;
+        const int y0 = (tile % p.tiles_per_frame) * p.rows_per_tile;
+        if (k >= 1) mbar_wait(bar(TAP_EMPTY), (k - 1) & 1);
+        mbar_expect_tx(bar(TAP_FULL), (uint32_t)p.ntaps * S::TAP_BYTES);
+        for (int t = 0; t < p.ntaps; ++t)
+          tma_load_4d(sbase + S::OFF_TAPS + t * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(TAP_FULL));
+        if (full) {
+          const int xb = k & 1;
+          if (k >= 2) mbar_wait(bar(X_EMPTY0 + xb), ((k >> 1) - 1) & 1);
+          mbar_expect_tx(bar(X_FULL0 + xb), S::XBUF);
+          for (int s = 0; s < S::NSUB; ++s)
+            tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + xb));
+        }
+      }
     }
-    mbar_wait(bar_full, ph_full);
-    ph_full ^= 1;
-    // ---- 2. conv: D1[128 x CI] = sum over taps, K = CI per tap
-    if (tid == 0) {
-      tc_fence_after();
-      for (int t = 0; t < p.ntaps; ++t)
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      auto issue_conv = [&](int k) {
+        const int b = k & 1;
+        mbar_wait(bar(TAP_FULL), k & 1);
+        if (k >= 2) mbar_wait(bar(D1_EMPTY0 + b), ((k >> 1) - 1) & 1);
+        tc_fence_after();
+        for (int t = 0; t < p.ntaps; ++t)
 #pragma unroll
-        for (int k = 0; k < CI / 16; ++k)
-          umma_bf16(tmem + COL_D1, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP_BYTES + k * 32),
-                    smem_desc<RB>(sbase + S::OFF_W2 + t * S::W2_TAP + k * 32), IDESC_CONV, (t | k) != 0);
-      umma_commit(bar_mma);
+          for (int kk = 0; kk < CI / 16; ++kk)
+            umma_bf16(tmem + S::COL_D1 + b * CI, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP_BYTES + kk * 32),
+                      smem_desc<RB>(sbase + S::OFF_W2 + t * S::W2_TAP + kk * 32), IDESC_CONV, (t | kk) != 0);
+        umma_commit(bar(TAP_EMPTY));
+        umma_commit(bar(D1_FULL0 + b));
+      };
+      mbar_wait(bar(W_FULL), 0);
+      if (T > 0) issue_conv(0);
+      for (int k = 0; k < T; ++k) {
+        if (full) {
+          mbar_wait(bar(E2_FULL), k & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < CI / 16; ++kk)
+            umma_bf16(tmem + S::COL_D2, smem_desc<RB>(sbase + S::OFF_E2 + kk * 32),
+                      smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), IDESC_EXP, kk != 0);
+          umma_commit(bar(D2_FULL));
+        }
+        if (k + 1 < T) issue_conv(k + 1);
+        if (full && p.has_next) {
+          const uint32_t xs = sbase + S::OFF_X + (k & 1) * S::XBUF;
+          mbar_wait(bar(Y_FULL), k & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < C / 16; ++kk)
+            umma_bf16(tmem + S::COL_D3, smem_desc<128>(xs + (kk / 4) * S::XSUB + (kk % 4) * 32),
+                      smem_desc<128>(sbase + S::OFF_W1 + (kk / 4) * S::W1_SUB + (kk % 4) * 32), IDESC_PROJ, kk != 0);
+          umma_commit(bar(D3_FULL));
+        }
+      }
     }
-    mbar_wait(bar_mma, ph_mma);
-    ph_mma ^= 1;
-    tc_fence_after();
-    // ---- 3. epilogue 1: +bias, PReLU, bf16 -> e2 tile (A operand of the expansion) or global
-    {
-      float v[CI];
-      if constexpr (CI == 32) tmem_ld32(tm_lane + COL_D1, v); else tmem_ld16(tm_lane + COL_D1, v);
+  } else {
+    // ============================================================ epilogue (warps 2..5)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;             // row of the tile = pixel = TMEM lane
+    const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
+    const bool storer = (warp == 2 && lane == 0);
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int b = k & 1;
+      // ---- epilogue 1: +bias, PReLU, bf16 -> e2 tile (A operand of the expansion) or global
+      {
+        float v[CI];
+        mbar_wait(bar(D1_FULL0 + b), (k >> 1) & 1);
+        tc_fence_after();
+        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D1 + b * CI, v); else tmem_ld16(tm_lane + S::COL_D1 + b * CI, v);
+        tc_fence_before();
+        mbar_arrive(bar(D1_EMPTY0 + b));
 #pragma unroll
-      for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b2[j], a2[j]);
-      if (p.conv_only) {
-        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b2[j], a2[j]);
+        if (!full) {
+          uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
 #pragma unroll
-        for (int c = 0; c < CI / 8; ++c)
-          o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                            pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-      } else {
+          for (int c = 0; c < CI / 8; ++c)
+            o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                              pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+          continue;
+        }
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
           *reinterpret_cast<uint4*>(smem + S::OFF_E2 + swz<RB>(m * RB + c * 16)) =
               make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
                          pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
         fence_proxy_async();
+        mbar_arrive(bar(E2_FULL));
       }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (p.conv_only) continue;
-    // ---- 4. expansion: D2[128 x C] = e2[128 x CI] * W3^T
-    if (tid == 0) {
+      // ---- epilogue 2: +bias, PReLU, + residual, PReLU, bf16 -> y tile (in place over x)
+      uint8_t* xt = smem + S::OFF_X + b * S::XBUF;
+      mbar_wait(bar(X_FULL0 + b), (k >> 1) & 1);
+      mbar_wait(bar(D2_FULL), k & 1);
       tc_fence_after();
-#pragma unroll
-      for (int k = 0; k < CI / 16; ++k)
-        umma_bf16(tmem + COL_D2, smem_desc<RB>(sbase + S::OFF_E2 + k * 32), smem_desc<RB>(sbase + S::OFF_W3 + k * 32),
-                  IDESC_EXP, k != 0);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, ph_mma);
-    ph_mma ^= 1;
-    tc_fence_after();
-    // ---- 5. epilogue 2: +bias, PReLU, + residual, PReLU, bf16 -> y tile (in place over x)
 #pragma unroll 1
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      float v[32];
-      tmem_ld32(tm_lane + COL_D2 + c0, v);
-      uint8_t* xrow = smem + S::OFF_X + (c0 / 64) * S::XSUB;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        float v[32];
+        tmem_ld32(tm_lane + S::COL_D2 + c0, v);
+        uint8_t* xrow = xt + (c0 / 64) * S::XSUB;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 channels
-        const int ch = c0 + 8 * c;
-        uint4* px = reinterpret_cast<uint4*>(xrow + swz<128>(m * 128 + ((ch % 64) / 8) * 16));
-        uint4 xr = *px;
-        const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
-        float o[8];
+        for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 channels
+          const int ch = c0 + 8 * c;
+          uint4* px = reinterpret_cast<uint4*>(xrow + swz<128>(m * 128 + ((ch % 64) / 8) * 16));
+          uint4 xr = *px;
+          const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
+          float o[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float2 xf = __bfloat1622float2(xh[q]);
-          int j = 8 * c + 2 * q;
-          o[2 * q] = prelu_f(prelu_f(v[j] + b3[c0 + j], a3[c0 + j]) + xf.x, aout[c0 + j]);
-          o[2 * q + 1] = prelu_f(prelu_f(v[j + 1] + b3[c0 + j + 1], a3[c0 + j + 1]) + xf.y, aout[c0 + j + 1]);
+          for (int qq = 0; qq < 4; ++qq) {
+            float2 xf = __bfloat1622float2(xh[qq]);
+            int j = 8 * c + 2 * qq;
+            o[2 * qq] = prelu_f(prelu_f(v[j] + b3[c0 + j], a3[c0 + j]) + xf.x, aout[c0 + j]);
+            o[2 * qq + 1] = prelu_f(prelu_f(v[j + 1] + b3[c0 + j + 1], a3[c0 + j + 1]) + xf.y, aout[c0 + j + 1]);
+          }
+          *px = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
         }
-        *px = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
       }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- 6. y tile -> global (TMA store) and the next block's projection on it
-    if (tid == 0) {
-      for (int s = 0; s < S::NSUB; ++s) tma_store_2d(&map_y, sbase + S::OFF_X + s * S::XSUB, s * 64, tile * 128);
-      tma_store_commit();
-      if (p.has_next) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < C / 16; ++k)
-          umma_bf16(tmem + COL_D3, smem_desc<128>(sbase + S::OFF_X + (k / 4) * S::XSUB + (k % 4) * 32),
-                    smem_desc<128>(sbase + S::OFF_W1 + (k / 4) * S::W1_SUB + (k % 4) * 32), IDESC_PROJ, k != 0);
-        umma_commit(bar_mma);
-      }
-    }
-    if (p.has_next) {
-      mbar_wait(bar_mma, ph_mma);
-      ph_mma ^= 1;
-      tc_fence_after();
-      float v[CI];
-      if constexpr (CI == 32) tmem_ld32(tm_lane + COL_D3, v); else tmem_ld16(tm_lane + COL_D3, v);
-#pragma unroll
-      for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
-      uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
-#pragma unroll
-      for (int c = 0; c < CI / 8; ++c)
-        o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                          pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+      fence_proxy_async();
       tc_fence_before();
+      mbar_arrive(bar(Y_FULL));
+      // ---- y tile -> global (TMA store by one thread once every row is written)
+      if (storer) {
+        mbar_wait(bar(Y_FULL), k & 1);
+        for (int s = 0; s < S::NSUB; ++s)
+          tma_store_2d(&map_y, sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, s * 64, tile * 128);
+        tma_store_commit();
+      }
+      // ---- epilogue 3: the next block's projection: +bias, PReLU, bf16 -> e1' (global)
+      if (p.has_next) {
+        mbar_wait(bar(D3_FULL), k & 1);
+        tc_fence_after();
+        float v[CI];
+        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D3, v); else tmem_ld16(tm_lane + S::COL_D3, v);
+        tc_fence_before();
+#pragma unroll
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
+        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
+#pragma unroll
+        for (int c = 0; c < CI / 8; ++c)
+          o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                            pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+      }
+      // the x/y buffer may be reloaded once the store has read it (and the projection MMAs,
+      // which the D3_FULL wait above covers, have consumed it)
+      if (storer) {
+        tma_store_wait_read();
+        mbar_arrive(bar(X_EMPTY0 + b));
+      }
     }
-    // the x/y tile is reloaded by the next iteration: the store must have read it out first
-    if (tid == 0) tma_store_wait_read();
-    __syncthreads();
+    if (storer) tma_store_wait_all();
   }
   // ---- teardown
-  if (tid == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(S::TMEM_COLS));
   }
 }
 
@@ -500,7 +556,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
     attr_done = true;
   }
   int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  k_umma_bottleneck<C, CI><<<grid, 128, smem, s>>>(me1, mx, my, p);
+  k_umma_bottleneck<C, CI><<<grid, 192, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }
 

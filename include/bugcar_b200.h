@@ -77,8 +77,9 @@ int bc_abi_version(void);
 int bc_load_enet(bc_ctx* ctx, const void* h_blob, size_t n_bytes);
 int bc_num_classes(const bc_ctx* ctx);
 int bc_set_precision(bc_ctx* ctx, int precision /* enum bc_precision */);
-/* Frames of a batch are pushed through the network `frames` at a time so that the
- * inter-layer activations stay resident in the 126 MB L2.  0 restores the default. */
+/* Frames of a batch are pushed through the network `frames` at a time (smaller chunks keep
+ * the inter-layer activations resident in the 126 MB L2, larger ones amortise launches).
+ * 0 restores the default: the whole batch in one pass. */
 int bc_set_chunk(bc_ctx* ctx, int frames);
 /* 1 (default): regular bottlenecks run as fused tcgen05 kernels in bf16 mode;
  * 0: every layer runs on the CUDA-core kernels (bring-up / A-B comparison). */
