@@ -96,6 +96,7 @@ struct bc_ctx {
   float *d_init_w = nullptr, *d_init_g = nullptr, *d_init_b = nullptr, *d_init_a = nullptr;
   std::vector<Bottleneck> blocks;
   float* d_full_w = nullptr;
+  uint8_t* d_head_umma = nullptr;     // tcgen05 operand image of the head (bf16 mode, C <= 16)
   // normalisation LUTs (models.py:91): [256][3] RGB order
   float* d_lut32 = nullptr;
   double* d_lut64 = nullptr;
@@ -381,6 +382,8 @@ int build_host_net(bc_ctx* c, const Container& ct) {
 void free_net(bc_ctx* c) {
   for (Bottleneck& b : c->blocks) { umma_free(b.um_a); umma_free(b.um_b); }
   for (void* p : c->dev_allocs) cudaFree(p);
+  if (c->d_head_umma) cudaFree(c->d_head_umma);
+  c->d_head_umma = nullptr;
   c->dev_allocs.clear();
   c->blocks.clear();
   c->d_init_w = c->d_init_g = c->d_init_b = c->d_init_a = c->d_full_w = nullptr;
@@ -464,6 +467,12 @@ int upload_net(bc_ctx* c) {
                         hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
+    }
+    if (c->num_classes <= 16) {
+      std::vector<float> hw(c->h_full_w.size());
+      for (size_t i = 0; i < hw.size(); ++i) hw[i] = bf16_round(c->h_full_w[i]);
+      if (!head_build(&c->d_head_umma, hw.data(), c->num_classes, 16))
+        return fail(c, BC_ERR_CUDA, "building the tcgen05 head operands failed");
     }
     c->umma_ready = true;
   }
@@ -603,6 +612,15 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       std::swap(X, Y);
     }
     if (block_index++ == stop_after) { launch_export_nchw<T>(X, dump, n, b.cout, H, W, s); return BC_OK; }
+  }
+  if (labels && c->tensor_cores && c->umma_ready && c->d_head_umma) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      cudaError_t ce = cudaSuccess;
+      L(c, "umma_head_argmax_lut", n * (32768.0 * 16 * esz + 131072.0), n * 2.0 * 32768 * 64 * 64, s,
+        [&] { ce = launch_umma_head((const bf16*)X, n, c->num_classes, c->d_head_umma, labels, *lut, c->num_sms, s); });
+      if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 head launch: ") + cudaGetErrorString(ce));
+      return BC_OK;
+    }
   }
   L(c, labels ? "head_tconv_argmax_lut" : "head_tconv_logits",
     n * (32768.0 * 16 * esz + (labels ? 131072.0 : 131072.0 * 4 * c->num_classes)), n * 2.0 * 32768 * 9 * 16 * c->num_classes, s,

@@ -93,6 +93,11 @@ void umma_free(UmmaPack& p);
 cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n,
                         int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
 
+// Head on tcgen05 (umma_head.cu): transposed conv 16 -> C (C <= 16) + argmax + LUT -> labels
+bool head_build(uint8_t** out, const float* w, int C, int CP);
+cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,
+                             int num_sms, cudaStream_t s);
+
 // ------------------------------------------------------------------ launchers (prepost.cu)
 struct ResizeTab {          // device tables for cv2.resize INTER_LINEAR, one (h,w)
   int src_h = 0, src_w = 0;

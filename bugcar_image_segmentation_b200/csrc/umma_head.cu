@@ -1,0 +1,187 @@
+// ENet head on tcgen05: ConvTranspose2d(16, C, 3, stride 2, padding 1, output_padding 1) +
+// per-pixel class argmax + class LUT (models.py:43-44 tail, models.py:55-58,67 / 78-81), one
+// kernel, bf16 operands, fp32 accumulation, 1 byte per output pixel leaves the SM.
+//
+// Each INPUT pixel (i, j) of the 128x256 map produces the 2x2 output quad (2i+qy, 2j+qx) from
+// its four neighbours (i+di, j+dj): as a GEMM, M = 128 input pixels, K = 4 neighbours x 16
+// channels, N = 4 quad positions x 16 classes, with the taps that do not reach a quad position
+// stored as zeros in B.  Every neighbour slab is one TMA box load of the NHWC activation
+// (shifted by (di, dj); out-of-bounds rows / columns zero-filled = the transposed conv's edge).
+//
+// Warp roles as in enet_umma.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+// (one TMEM lane = one input pixel per thread; 64 fp32 logits -> 4 labels).  Taps and the
+// accumulator are double buffered.
+#include "umma_common.cuh"
+
+#include <cstring>
+
+namespace bc {
+
+struct HeadParams {
+  int num_tiles;            // B * 128 rows * 2 half-rows
+  int C;                    // classes (<= 16)
+  const uint8_t* wblob;     // [4 taps][64 rows = q*16+class][16 k] bf16, 32-byte swizzled rows
+  uint8_t* labels;          // (B,256,512)
+  Lut256 lut;
+};
+
+static constexpr int HEAD_TAP = 128 * 32;      // one neighbour slab: 128 px x 16 ch bf16
+static constexpr int HEAD_WTAP = 64 * 32;      // one tap of B
+static constexpr int HEAD_OFF_TAPS = 0;        // 2 sets x 4 taps
+static constexpr int HEAD_OFF_W = 2 * 4 * HEAD_TAP;
+static constexpr int HEAD_OFF_LUT = HEAD_OFF_W + 4 * HEAD_WTAP;
+static constexpr int HEAD_OFF_BAR = HEAD_OFF_LUT + 256;
+static constexpr int HEAD_SMEM = HEAD_OFF_BAR + 128;
+
+__global__ void __launch_bounds__(192, 1)
+k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][128][16], 32-byte swizzle
+            const HeadParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + HEAD_OFF_BAR);
+  enum { TAP_FULL0 = 0, TAP_FULL1, TAP_EMPTY0, TAP_EMPTY1, D_FULL0, D_FULL1, D_EMPTY0, D_EMPTY1, W_FULL, NBARS };
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
+  uint8_t* slut = smem + HEAD_OFF_LUT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    const int one[] = {TAP_FULL0, TAP_FULL1, TAP_EMPTY0, TAP_EMPTY1, D_FULL0, D_FULL1, W_FULL};
+    for (int b : one) mbar_init(bar(b), 1);
+    mbar_init(bar(D_EMPTY0), 128);
+    mbar_init(bar(D_EMPTY1), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar(W_FULL), 4 * HEAD_WTAP);
+    bulk_load(sbase + HEAD_OFF_W, p.wblob, 4 * HEAD_WTAP, bar(W_FULL));
+  }
+  for (int i = tid; i < 256; i += 192) slut[i] = p.lut.v[i];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t IDESC = instr_desc(128, 64);
+  const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < T; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int n = tile >> 8, y = (tile & 255) >> 1, x0 = (tile & 1) * 128;
+        const int b = k & 1;
+        if (k >= 2) mbar_wait(bar(TAP_EMPTY0 + b), ((k >> 1) - 1) & 1);
+        mbar_expect_tx(bar(TAP_FULL0 + b), 4 * HEAD_TAP);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          tma_load_4d(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP, &map_x, 0, x0 + (t & 1), y + (t >> 1), n,
+                      bar(TAP_FULL0 + b));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar(W_FULL), 0);
+      for (int k = 0; k < T; ++k) {
+        const int b = k & 1;
+        mbar_wait(bar(TAP_FULL0 + b), (k >> 1) & 1);
+        if (k >= 2) mbar_wait(bar(D_EMPTY0 + b), ((k >> 1) - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          umma_bf16(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP),
+                    smem_desc<32>(sbase + HEAD_OFF_W + t * HEAD_WTAP), IDESC, t != 0);
+        umma_commit(bar(TAP_EMPTY0 + b));
+        umma_commit(bar(D_FULL0 + b));
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int C = p.C;
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int n = tile >> 8, y = (tile & 255) >> 1, x = (tile & 1) * 128 + m;
+      const int b = k & 1;
+      mbar_wait(bar(D_FULL0 + b), (k >> 1) & 1);
+      tc_fence_after();
+      float v0[32], v1[32];
+      tmem_ld32(tm_lane + b * 64, v0);
+      tmem_ld32(tm_lane + b * 64 + 32, v1);
+      tc_fence_before();
+      mbar_arrive(bar(D_EMPTY0 + b));
+      uint8_t lab[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* v = q < 2 ? v0 + 16 * q : v1 + 16 * (q - 2);
+        float best = v[0];
+        int bi = 0;
+#pragma unroll
+        for (int c = 1; c < 16; ++c)
+          if (c < C && v[c] > best) { best = v[c]; bi = c; }      // first maximum wins (models.py:55)
+        lab[q] = slut[bi];
+      }
+      uint8_t* o = p.labels + ((size_t)(n * 256 + 2 * y) * 512 + 2 * x);
+      *reinterpret_cast<uchar2*>(o) = make_uchar2(lab[0], lab[1]);
+      *reinterpret_cast<uchar2*>(o + 512) = make_uchar2(lab[2], lab[3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+  }
+}
+
+// B image: for neighbour tap (di, dj), row q*16 + class, k = input channel:
+//   W[k][class][ky][kx] when the neighbour reaches quad (qy, qx) (di <= qy, dj <= qx) with
+//   ky = qy ? (di ? 0 : 2) : 1, kx = qx ? (dj ? 0 : 2) : 1;  zero otherwise.
+// w: the folded head weights [ky*3+kx][16][CP] (api.cu), already rounded to bf16 values.
+bool head_build(uint8_t** out, const float* w, int C, int CP) {
+  std::vector<uint8_t> img(4 * HEAD_WTAP, 0);
+  for (int t = 0; t < 4; ++t) {
+    int di = t >> 1, dj = t & 1;
+    for (int q = 0; q < 4; ++q) {
+      int qy = q >> 1, qx = q & 1;
+      if (di > qy || dj > qx) continue;
+      int ky = qy ? (di ? 0 : 2) : 1, kx = qx ? (dj ? 0 : 2) : 1;
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 16; ++k) {
+          __nv_bfloat16 h = __float2bfloat16_rn(w[((size_t)(ky * 3 + kx) * 16 + k) * CP + c]);
+          uint32_t off = (uint32_t)((q * 16 + c) * 32 + k * 2);
+          memcpy(img.data() + t * HEAD_WTAP + swz<32>(off), &h, 2);
+        }
+    }
+  }
+  if (cudaMalloc(out, img.size()) != cudaSuccess) return false;
+  return cudaMemcpy(*out, img.data(), img.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,
+                             int num_sms, cudaStream_t s) {
+  CUtensorMap mx;
+  if (!make_map_e1(&mx, x, B, 128, 256, 16)) return cudaErrorInvalidValue;
+  HeadParams p{};
+  p.num_tiles = B * 256;
+  p.C = C;
+  p.wblob = wblob;
+  p.labels = labels;
+  p.lut = lut;
+  static bool attr_done = false;
+  const int smem = HEAD_SMEM + 1024;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_head, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  k_umma_head<<<grid, 192, smem, s>>>(mx, p);
+  return cudaGetLastError();
+}
+
+}  // namespace bc

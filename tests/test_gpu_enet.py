@@ -129,7 +129,15 @@ def test_bf16_logits_and_argmax(setup):
         assert conf >= 0.999, conf
         # fused head (argmax + LUT inside the kernel) == argmax + LUT of this mode's logits
         lab = m.predict(setup["x"])
-        assert np.array_equal(lab, pre_oracle.labels_from_logits(got, pre_oracle.LUT_3WAY))
+        ref_lab = pre_oracle.labels_from_logits(got, pre_oracle.LUT_3WAY)
+        if tc == 0:
+            assert np.array_equal(lab, ref_lab)       # same kernel, same arithmetic
+        else:
+            # the tcgen05 head accumulates in a different order than the CUDA-core logits kernel:
+            # labels may differ only where the top-2 logits are within fp32 round-off of each other
+            diff = lab != ref_lab
+            assert diff.mean() <= 1e-4, diff.mean()
+            assert (_margin(got)[diff] <= 1e-4 * scale).all()
     if setup["which"] == "trained":
         # a trained-like network keeps its decisions under bf16 storage
         assert raw32 >= 0.99, raw32
