@@ -448,6 +448,18 @@ int upload_net(bc_ctx* c) {
   if (bf && umma_available()) {
     for (size_t i = 0; i < c->blocks.size(); ++i) {
       Bottleneck& b = c->blocks[i];
+      if (b.kind == 3) {     // upsampling bottleneck (+ the next regular block's projection when it is 64 wide)
+        const HostBlock& hb = c->h_blocks[i];
+        const HostBlock* nx = nullptr;
+        if (b.cout == 64 && i + 1 < c->blocks.size() && umma_supported(c->blocks[i + 1]) && c->blocks[i + 1].cin == 64)
+          nx = &c->h_blocks[i + 1];
+        if (!up_build(b.um_a, b.cin, b.ci, b.cout, hb.cm.w.data(), hb.cm.bias.data(), hb.c1.w.data(), hb.c1.bias.data(),
+                      hb.c1.alpha.data(), hb.c2.w.data(), hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
+                      hb.c3.bias.data(), hb.alpha_out.data(), nx ? nx->c1.w.data() : nullptr,
+                      nx ? nx->c1.bias.data() : nullptr, nx ? nx->c1.alpha.data() : nullptr))
+          return fail(c, BC_ERR_CUDA, "building the tcgen05 upsampling operands failed");
+        continue;
+      }
       if (!umma_supported(b)) continue;
       const HostBlock& hb = c->h_blocks[i];
       const HostBlock* nx = nullptr;
@@ -603,11 +615,28 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       std::swap(X, Y);
     } else {
       const uint8_t* idx = b.cout == 16 ? c->idx1 : c->idx2;   // upsample5_0 pairs with downsample1_0
-      conv("up_proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
       double px = (double)n * H * W;
+      bool done = false;
+      if (c->tensor_cores && c->umma_ready && b.um_a.wblob) {
+        if constexpr (std::is_same<T, bf16>::value) {
+          cudaError_t ce = cudaSuccess;
+          const int has_next = b.um_a.has_next ? 1 : 0;
+          L(c, b.cout == 64 ? "umma_up4" : "umma_up5", px * (b.cin * esz + b.cout + 4.0 * b.cout * esz + has_next * 4.0 * 16 * esz),
+            2.0 * px * ((double)b.cin * (b.cout + b.ci) + 4.0 * b.ci * b.ci + 4.0 * b.ci * b.cout + has_next * 4.0 * 64 * 16), s,
+            [&] { ce = launch_umma_up(b.um_a, b.cin, b.cout, (const bf16*)X, idx, (bf16*)Y, (bf16*)E1, n, H, W, has_next,
+                                      c->num_sms, s); });
+          if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 upsampling launch: ") + cudaGetErrorString(ce));
+          e1_ready = has_next != 0;
+          done = true;
+        }
+      }
+      if (!done) {
+      e1_ready = false;
+      conv("up_proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
       L(c, "up_unpool_tconv_expand", px * ((b.cin + b.ci) * esz + b.cout + 4.0 * b.cout * esz),
         2.0 * px * ((double)b.cin * b.cout + 4.0 * b.ci * b.ci + 4.0 * b.ci * b.cout), s,
         [&] { launch_up_b<T>(X, E1, idx, Y, b, n, H, W, s); });
+      }
       H *= 2; W *= 2;
       std::swap(X, Y);
     }

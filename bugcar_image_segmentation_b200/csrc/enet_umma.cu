@@ -331,6 +331,18 @@ bool make_map_x(CUtensorMap* m, const bf16* base, size_t pixels, int C) {
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2D map over [pixels][C] bf16; box = [box_px][C] (whole pixel rows), swizzle = C * 2 bytes
+bool make_map_rows(CUtensorMap* m, const bf16* base, size_t pixels, int C, int box_px, int sw) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)box_px};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle_for(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool umma_available() { return encode_fn() != nullptr; }
 
 bool umma_supported(const Bottleneck& bn) {

@@ -93,6 +93,13 @@ void umma_free(UmmaPack& p);
 cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n,
                         int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
 
+// Upsampling bottleneck on tcgen05 (umma_up.cu)
+bool up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const float* bm, const float* w1, const float* b1,
+              const float* a1, const float* wt, const float* bt, const float* at, const float* w3, const float* b3,
+              const float* aout, const float* w1n, const float* b1n, const float* a1n);
+cudaError_t launch_umma_up(const UmmaPack& pk, int cin, int cout, const bf16* x, const uint8_t* idx, bf16* y, bf16* e1_next,
+                           int n, int Hl, int Wl, int has_next, int num_sms, cudaStream_t s);
+
 // Head on tcgen05 (umma_head.cu): transposed conv 16 -> C (C <= 16) + argmax + LUT -> labels
 bool head_build(uint8_t** out, const float* w, int C, int CP);
 cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,

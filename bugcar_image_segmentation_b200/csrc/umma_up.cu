@@ -1,0 +1,386 @@
+// ENet upsampling bottleneck on tcgen05 (bf16 operands, fp32 accumulation), one kernel:
+//
+//   x tile (128 low-res pixels, TMA) --G1--> [ main = Wm x | e1 = W1 x ]         D_a [128 x (COUT+CI)]
+//        e1: +bias, act, bf16 -> smem             --G2--> 4 taps of the 2x2 stride-2 transposed conv  D_b [128 x 4 CI]
+//        e2_t: +bias, act, bf16 -> smem (4 tiles) --G3--> e3_t = W3 e2_t          D_c [4][128 x COUT]
+//        out(2y+ky, 2x+kx) = act_out(e3_t + b3 + (pool index == t ? main + bm : 0))   (max-unpool)
+//          -> bf16 -> smem, staged as whole high-resolution rows -> TMA store
+//        (optional) the next block's 1x1 projection on the staged rows  --G4--> e1' -> global
+//
+// One TMEM lane = one low-resolution pixel; the four output pixels of a thread differ only in
+// which quarter of D_c they read.  Semantics: oracle/enet_oracle.py `up` (the upsampling
+// bottlenecks of the frozen graph the reference runs, models.py:43-44).
+#include "umma_common.cuh"
+
+#include <cstring>
+
+namespace bc {
+
+struct UpParams {
+  int num_tiles;          // low-resolution 128-pixel tiles
+  int tiles_per_frame;    // Hl * Wl / 128
+  int Wl;                 // low-resolution width (64 or 128)
+  int has_next;
+  const uint8_t* idx;     // [low px][COUT] pool window position (2 bits)
+  bf16* e1_next;          // [high px][16]
+  const uint8_t* wblob;
+  const float* fparams;   // bm[COUT] b1[CI] a1[CI] bt[CI] at[CI] b3[COUT] aout[COUT] b1n[16] a1n[16]
+};
+
+template <int CIN, int CI, int COUT>
+struct UpSmem {
+  static constexpr int RB = CI * 2;                    // row bytes of CI-wide operands
+  static constexpr int ORB = COUT * 2;                 // bytes per output pixel (128 or 32)
+  static constexpr int NSUB = CIN / 64;
+  static constexpr int XSUB = 128 * 128;
+  static constexpr int XBUF = NSUB * XSUB;
+  static constexpr int N1 = COUT + CI;
+  static constexpr int E_TILE = 128 * RB;
+  static constexpr int OUT_BYTES = 512 * ORB;          // 512 high-res pixels per tile
+  static constexpr int OUT_ROW = COUT == 64 ? 128 * ORB : 256 * ORB;   // one staged high-res row
+  static constexpr int NROWS = OUT_BYTES / OUT_ROW;    // 4 (up4) or 2 (up5)
+  static constexpr int B1_SUB = N1 * 128;
+  static constexpr int WT_BYTES = 4 * CI * RB;
+  static constexpr int W3_BYTES = COUT * RB;
+  static constexpr int W1N_BYTES = 16 * 128;           // next projection [16][64] (COUT == 64 only)
+  static constexpr int OFF_X = 0;                      // 2 buffers
+  static constexpr int OFF_E1 = OFF_X + 2 * XBUF;
+  static constexpr int OFF_E2 = OFF_E1 + ((E_TILE + 1023) / 1024) * 1024;
+  static constexpr int OFF_OUT = OFF_E2 + 4 * E_TILE;
+  static constexpr int OFF_W = OFF_OUT + OUT_BYTES;
+  static constexpr int OFF_B1 = OFF_W;
+  static constexpr int OFF_WT = OFF_B1 + ((NSUB * B1_SUB + 1023) / 1024) * 1024;
+  static constexpr int OFF_W3 = OFF_WT + ((WT_BYTES + 1023) / 1024) * 1024;
+  static constexpr int OFF_W1N = OFF_W3 + ((W3_BYTES + 1023) / 1024) * 1024;
+  static constexpr int W_BYTES = OFF_W1N - OFF_W + W1N_BYTES;
+  static constexpr int OFF_F = OFF_W + ((W_BYTES + 1023) / 1024) * 1024;
+  static constexpr int NF = 3 * COUT + 4 * CI + 32;
+  static constexpr int OFF_BAR = OFF_F + ((NF * 4 + 63) / 64) * 64;
+  static constexpr int TOTAL = OFF_BAR + 192;
+  static constexpr uint32_t COL_A = 0, COL_B = N1, COL_C = N1 + 4 * CI, COL_D = COL_B;
+  static constexpr uint32_t TMEM_COLS = (N1 + 4 * CI + 4 * COUT) <= 256 ? 256 : 512;
+};
+
+template <int CIN, int CI, int COUT>
+__global__ void __launch_bounds__(192, 1)
+k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box [128][64], 128-byte swizzle
+          const __grid_constant__ CUtensorMap map_y,   // 2D [high px][COUT], box = one staged row
+          const UpParams p) {
+  using S = UpSmem<CIN, CI, COUT>;
+  constexpr int RB = S::RB, ORB = S::ORB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  float* sf = (float*)(smem + S::OFF_F);
+  const float *bm = sf, *b1 = bm + COUT, *a1 = b1 + CI, *bt = a1 + CI, *at = bt + CI, *b3 = at + CI, *aout = b3 + COUT,
+              *b1n = aout + COUT, *a1n = b1n + 16;
+  uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
+  enum { X_FULL0 = 0, X_FULL1, X_EMPTY0, X_EMPTY1, DA_FULL, E1_FULL, DB_FULL, E2_FULL, DC_FULL, OUT_FULL, OUT_EMPTY,
+         DD_FULL, W_FULL, NBARS };
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    const int one[] = {X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, DA_FULL, DB_FULL, DC_FULL, OUT_EMPTY, DD_FULL, W_FULL};
+    for (int b : one) mbar_init(bar(b), 1);
+    const int all[] = {E1_FULL, E2_FULL, OUT_FULL};
+    for (int b : all) mbar_init(bar(b), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar(W_FULL), S::W_BYTES + S::NF * 4);
+    bulk_load(sbase + S::OFF_W, p.wblob, S::W_BYTES, bar(W_FULL));
+    bulk_load(sbase + S::OFF_F, p.fparams, S::NF * 4, bar(W_FULL));
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int rows_lo = 128 / p.Wl;                       // low-res rows per tile (2 or 1)
+  const int Wh = 2 * p.Wl;                              // high-res width
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int k = 0; k < T; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int b = k & 1;
+        if (k >= 2) mbar_wait(bar(X_EMPTY0 + b), ((k >> 1) - 1) & 1);
+        mbar_expect_tx(bar(X_FULL0 + b), S::XBUF);
+        for (int s = 0; s < S::NSUB; ++s)
+          tma_load_2d(sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + b));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar(W_FULL), 0);
+      for (int k = 0; k < T; ++k) {
+        const int b = k & 1;
+        // G1: [main | e1] = x * B1^T
+        mbar_wait(bar(X_FULL0 + b), (k >> 1) & 1);
+        if (k >= 1) mbar_wait(bar(OUT_FULL), (k - 1) & 1);       // epilogue done reading main of tile k-1
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < CIN / 16; ++kk)
+          umma_bf16(tmem + S::COL_A, smem_desc<128>(sbase + S::OFF_X + b * S::XBUF + (kk / 4) * S::XSUB + (kk % 4) * 32),
+                    smem_desc<128>(sbase + S::OFF_B1 + (kk / 4) * S::B1_SUB + (kk % 4) * 32), instr_desc(128, S::N1), kk != 0);
+        umma_commit(bar(X_EMPTY0 + b));
+        umma_commit(bar(DA_FULL));
+        // G2: the four transposed-conv taps
+        mbar_wait(bar(E1_FULL), k & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < CI / 16; ++kk)
+          umma_bf16(tmem + S::COL_B, smem_desc<RB>(sbase + S::OFF_E1 + kk * 32), smem_desc<RB>(sbase + S::OFF_WT + kk * 32),
+                    instr_desc(128, 4 * CI), kk != 0);
+        umma_commit(bar(DB_FULL));
+        // G3: expansion of every tap
+        mbar_wait(bar(E2_FULL), k & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int kk = 0; kk < CI / 16; ++kk)
+            umma_bf16(tmem + S::COL_C + t * COUT, smem_desc<RB>(sbase + S::OFF_E2 + t * S::E_TILE + kk * 32),
+                      smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), instr_desc(128, COUT), kk != 0);
+        umma_commit(bar(DC_FULL));
+        // G4: next block's projection on the staged high-res rows (COUT == 64: one row = one M tile)
+        if constexpr (COUT == 64) {
+          if (p.has_next) {
+            mbar_wait(bar(OUT_FULL), k & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_bf16(tmem + S::COL_D + r * 16, smem_desc<128>(sbase + S::OFF_OUT + r * S::OUT_ROW + kk * 32),
+                          smem_desc<128>(sbase + S::OFF_W1N + kk * 32), instr_desc(128, 16), kk != 0);
+            umma_commit(bar(DD_FULL));
+          }
+        }
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+    const bool storer = (warp == 2 && lane == 0);
+    const int lr = m / p.Wl, lx = m % p.Wl;             // position of my low-res pixel inside the tile
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      // ---- E_A: e1 = act(proj + b1) -> smem
+      mbar_wait(bar(DA_FULL), k & 1);
+      tc_fence_after();
+      {
+        float v[CI];
+        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_A + COUT, v); else tmem_ld16(tm_lane + S::COL_A + COUT, v);
+#pragma unroll
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b1[j], a1[j]);
+#pragma unroll
+        for (int c = 0; c < CI / 8; ++c)
+          *reinterpret_cast<uint4*>(smem + S::OFF_E1 + swz<RB>(m * RB + c * 16)) =
+              make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                         pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(E1_FULL));
+      // ---- E_B: e2_t = act(tconv tap + bt) -> 4 smem tiles
+      mbar_wait(bar(DB_FULL), k & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        float v[CI];
+        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_B + t * CI, v); else tmem_ld16(tm_lane + S::COL_B + t * CI, v);
+#pragma unroll
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + bt[j], at[j]);
+#pragma unroll
+        for (int c = 0; c < CI / 8; ++c)
+          *reinterpret_cast<uint4*>(smem + S::OFF_E2 + t * S::E_TILE + swz<RB>(m * RB + c * 16)) =
+              make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                         pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(E2_FULL));
+      // ---- E_C: out = act_out(e3_t + b3 + unpooled main) -> staged high-res rows
+      mbar_wait(bar(DC_FULL), k & 1);
+      if (k >= 1) mbar_wait(bar(OUT_EMPTY), (k - 1) & 1);
+      tc_fence_after();
+      const uint8_t* ip = p.idx + ((size_t)tile * 128 + m) * COUT;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        float mainv[16];
+        tmem_ld16(tm_lane + S::COL_A + c0, mainv);
+        const uint4 iv = *reinterpret_cast<const uint4*>(ip + c0);
+        const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mainv[j] += bm[c0 + j];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float v[16];
+          tmem_ld16(tm_lane + S::COL_C + t * COUT + c0, v);
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float o0 = prelu_f(v[j] + b3[c0 + j] + (ib[j] == t ? mainv[j] : 0.f), aout[c0 + j]);
+            float o1 = prelu_f(v[j + 1] + b3[c0 + j + 1] + (ib[j + 1] == t ? mainv[j + 1] : 0.f), aout[c0 + j + 1]);
+            pk[j / 2] = pack_bf16(o0, o1);
+          }
+          // high-res pixel (2*lr + ky, 2*lx + kx) of this tile
+          const int hr = 2 * lr + (t >> 1), hx = 2 * lx + (t & 1);
+          uint8_t* orow = smem + S::OFF_OUT + (COUT == 64 ? hr * S::OUT_ROW : (t >> 1) * S::OUT_ROW);
+          const uint32_t off = (uint32_t)(hx * ORB + c0 * 2);
+          *reinterpret_cast<uint4*>(orow + swz<(COUT == 64 ? 128 : 32)>(off)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(orow + swz<(COUT == 64 ? 128 : 32)>(off + 16)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar(OUT_FULL));
+      if (storer) {
+        mbar_wait(bar(OUT_FULL), k & 1);
+        const int n = tile / p.tiles_per_frame;
+        const int y0 = (tile % p.tiles_per_frame) * rows_lo;          // first low-res row of the tile
+        const int hrow0 = n * (p.tiles_per_frame * rows_lo * 2) + 2 * y0;   // global high-res row index
+        for (int r = 0; r < S::NROWS; ++r)
+          tma_store_2d(&map_y, sbase + S::OFF_OUT + r * S::OUT_ROW, 0, (hrow0 + r) * Wh);
+        tma_store_commit();
+      }
+      // ---- E_D: next block's projection
+      if constexpr (COUT == 64) {
+        if (p.has_next) {
+          mbar_wait(bar(DD_FULL), k & 1);
+          tc_fence_after();
+          const int n = tile / p.tiles_per_frame;
+          const int y0 = (tile % p.tiles_per_frame) * rows_lo;
+          const size_t hrow0 = (size_t)n * (p.tiles_per_frame * rows_lo * 2) + 2 * y0;
+#pragma unroll 1
+          for (int r = 0; r < 4; ++r) {
+            float v[16];
+            tmem_ld16(tm_lane + S::COL_D + r * 16, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
+            uint4* o = reinterpret_cast<uint4*>(p.e1_next + ((hrow0 + r) * Wh + m) * 16);
+            o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+          }
+          tc_fence_before();
+        }
+      }
+      if (storer) {
+        tma_store_wait_read();
+        mbar_arrive(bar(OUT_EMPTY));
+      }
+    }
+    if (storer) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(S::TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------ host side
+static void put_rows(uint8_t* dst, int rows, int row_bytes, int sw, const float* w, size_t stride_row, size_t stride_k,
+                     int k0) {
+  // element (row r, k) = w[r * stride_row + (k0 + k) * stride_k]
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < row_bytes / 2; ++k) {
+      __nv_bfloat16 h = __float2bfloat16_rn(w[(size_t)r * stride_row + (size_t)(k0 + k) * stride_k]);
+      uint32_t off = (uint32_t)(r * row_bytes + k * 2);
+      uint32_t so = sw == 128 ? swz<128>(off) : sw == 64 ? swz<64>(off) : swz<32>(off);
+      memcpy(dst + so, &h, 2);
+    }
+}
+
+template <int CIN, int CI, int COUT>
+static bool up_build_t(UmmaPack& out, const float* wm, const float* bmv, const float* w1, const float* b1v, const float* a1v,
+                       const float* wt, const float* btv, const float* atv, const float* w3, const float* b3v,
+                       const float* aoutv, const float* w1n, const float* b1nv, const float* a1nv) {
+  using S = UpSmem<CIN, CI, COUT>;
+  std::vector<uint8_t> img(S::W_BYTES, 0);
+  // folded layouts are [tap][cin][cout]: element (out o, in k) = w[k * cout + o]
+  for (int s = 0; s < S::NSUB; ++s) {
+    uint8_t* d = img.data() + (S::OFF_B1 - S::OFF_W) + s * S::B1_SUB;
+    put_rows(d, COUT, 128, 128, wm, 1, COUT, s * 64);                       // rows 0..COUT-1: main conv
+    put_rows(d + COUT * 128, CI, 128, 128, w1, 1, CI, s * 64);              // rows COUT..: projection
+  }
+  for (int t = 0; t < 4; ++t)                                                // rows t*CI + j
+    put_rows(img.data() + (S::OFF_WT - S::OFF_W) + t * CI * S::RB, CI, S::RB, S::RB, wt + (size_t)t * CI * CI, 1, CI, 0);
+  put_rows(img.data() + (S::OFF_W3 - S::OFF_W), COUT, S::RB, S::RB, w3, 1, COUT, 0);
+  if (w1n) put_rows(img.data() + (S::OFF_W1N - S::OFF_W), 16, 128, 128, w1n, 1, 16, 0);
+  std::vector<float> f(S::NF, 0.f);
+  float* o = f.data();
+  memcpy(o, bmv, COUT * 4); o += COUT;
+  memcpy(o, b1v, CI * 4); o += CI;
+  memcpy(o, a1v, CI * 4); o += CI;
+  memcpy(o, btv, CI * 4); o += CI;
+  memcpy(o, atv, CI * 4); o += CI;
+  memcpy(o, b3v, COUT * 4); o += COUT;
+  memcpy(o, aoutv, COUT * 4); o += COUT;
+  if (w1n) { memcpy(o, b1nv, 16 * 4); memcpy(o + 16, a1nv, 16 * 4); }
+  if (cudaMalloc(&out.wblob, S::W_BYTES) != cudaSuccess) return false;
+  if (cudaMalloc(&out.fparams, f.size() * 4) != cudaSuccess) return false;
+  cudaMemcpy(out.wblob, img.data(), S::W_BYTES, cudaMemcpyHostToDevice);
+  cudaMemcpy(out.fparams, f.data(), f.size() * 4, cudaMemcpyHostToDevice);
+  out.C = CIN; out.CI = CI; out.ntaps = 4; out.has_exp = true; out.has_next = w1n != nullptr;
+  return true;
+}
+
+// NB: a row of put_rows' source walks `stride_row` = 1 (out channel contiguous in [cin][cout]).
+bool up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const float* bm, const float* w1, const float* b1,
+              const float* a1, const float* wt, const float* bt, const float* at, const float* w3, const float* b3,
+              const float* aout, const float* w1n, const float* b1n, const float* a1n) {
+  if (cin == 128 && ci == 32 && cout == 64)
+    return up_build_t<128, 32, 64>(out, wm, bm, w1, b1, a1, wt, bt, at, w3, b3, aout, w1n, b1n, a1n);
+  if (cin == 64 && ci == 16 && cout == 16)
+    return up_build_t<64, 16, 16>(out, wm, bm, w1, b1, a1, wt, bt, at, w3, b3, aout, nullptr, nullptr, nullptr);
+  return false;
+}
+
+template <int CIN, int CI, int COUT>
+static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t* idx, bf16* y, bf16* e1_next, int n, int Hl,
+                               int Wl, int has_next, int num_sms, cudaStream_t s) {
+  using S = UpSmem<CIN, CI, COUT>;
+  CUtensorMap mx, my;
+  const size_t lpx = (size_t)n * Hl * Wl;
+  if (!make_map_x(&mx, x, lpx, CIN)) return cudaErrorInvalidValue;
+  if (COUT == 64) { if (!make_map_x(&my, y, lpx * 4, 64)) return cudaErrorInvalidValue; }
+  else if (!make_map_rows(&my, y, lpx * 4, COUT, 256, 32)) return cudaErrorInvalidValue;
+  UpParams p{};
+  p.num_tiles = (int)(lpx / 128);
+  p.tiles_per_frame = Hl * Wl / 128;
+  p.Wl = Wl;
+  p.has_next = has_next;
+  p.idx = idx;
+  p.e1_next = e1_next;
+  p.wblob = pk.wblob;
+  p.fparams = pk.fparams;
+  static bool attr_done = false;
+  const int smem = S::TOTAL + 1024;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_up<CIN, CI, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  k_umma_up<CIN, CI, COUT><<<grid, 192, smem, s>>>(mx, my, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_umma_up(const UmmaPack& pk, int cin, int cout, const bf16* x, const uint8_t* idx, bf16* y, bf16* e1_next,
+                           int n, int Hl, int Wl, int has_next, int num_sms, cudaStream_t s) {
+  if (cin == 128 && cout == 64 && Wl == 64) return up_launch_t<128, 32, 64>(pk, x, idx, y, e1_next, n, Hl, Wl, has_next, num_sms, s);
+  if (cin == 64 && cout == 16 && Wl == 128) return up_launch_t<64, 16, 16>(pk, x, idx, y, e1_next, n, Hl, Wl, 0, num_sms, s);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace bc
