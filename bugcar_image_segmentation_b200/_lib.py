@@ -29,6 +29,7 @@ SIGNATURES = {
     "bc_set_chunk": (_i, [_vp, _i]),
     "bc_set_tensor_cores": (_i, [_vp, _i]),
     "bc_set_graphs": (_i, [_vp, _i]),
+    "bc_set_host_overlap": (_i, [_vp, _i]),
     "bc_set_bev": (_i, [_vp, C.POINTER(_d), _i, _i, _i, _i, _d]),
     "bc_resize_bgr": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "bc_preprocess": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
@@ -142,6 +143,9 @@ class Context:
 
     def set_graphs(self, on):
         self._ck(self.lib.bc_set_graphs(self.h, int(bool(on))))
+
+    def set_host_overlap(self, on):
+        self._ck(self.lib.bc_set_host_overlap(self.h, int(bool(on))))
 
     def set_bev(self, M, in_rows, in_cols, warp_w, warp_h, cm_per_px):
         m = (_d * 9)(*[float(v) for v in M])

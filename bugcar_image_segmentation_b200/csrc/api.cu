@@ -128,6 +128,12 @@ struct bc_ctx {
   // ---- CUDA graphs of bc_pipeline[_host]
   std::vector<GraphEntry> graphs;
 
+  // ---- host entry point: copy stream for H2D / compute overlap
+  int host_overlap = 1;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t call_start = nullptr;
+
   // ---- per-kernel profiling (bc_set_profile): one event pair per launch
   int profiling = 0;
   std::vector<ProfRec> prof;
@@ -922,6 +928,9 @@ void bc_destroy(bc_ctx* c) {
   for (auto& kv : c->resize_tabs) if (kv.second.blob) cudaFree(kv.second.blob);
   for (auto& r : c->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto e : c->copy_done) if (e) cudaEventDestroy(e);
+  if (c->call_start) cudaEventDestroy(c->call_start);
   void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out};
   for (void* p : ps) if (p) cudaFree(p);
   delete c;
@@ -974,6 +983,12 @@ int bc_set_tensor_cores(bc_ctx* c, int enable) {
 int bc_set_graphs(bc_ctx* c, int enable) {
   if (!c) return BC_ERR_ARG;
   c->use_graphs = enable ? 1 : 0;
+  return BC_OK;
+}
+
+int bc_set_host_overlap(bc_ctx* c, int enable) {
+  if (!c) return BC_ERR_ARG;
+  c->host_overlap = enable ? 1 : 0;
   return BC_OK;
 }
 
@@ -1156,9 +1171,43 @@ int bc_pipeline_host(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const
   const ResizeTab* rt;
   if ((r = get_resize_tab(c, h, w, &rt))) return r;   // may allocate: keep it out of capture
 
-  CU(cudaMemcpyAsync(c->d_frames_in, h_bgr, in_bytes, cudaMemcpyHostToDevice, s));
-  if ((r = run_pipeline(c, c->d_frames_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, c->d_grids_out, s))) return r;
-  CU(cudaMemcpyAsync(h_grids, c->d_grids_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  // Large batches go through in sub-batches so that the H2D copy of sub-batch i+1 (copy
+  // stream) overlaps the kernels of sub-batch i (caller's stream); grids return as they finish.
+  const int nsub = c->host_overlap ? (B >= 128 ? 4 : B >= 32 ? 2 : 1) : 1;
+  if (nsub == 1) {
+    CU(cudaMemcpyAsync(c->d_frames_in, h_bgr, in_bytes, cudaMemcpyHostToDevice, s));
+    if ((r = run_pipeline(c, c->d_frames_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, c->d_grids_out, s))) return r;
+    CU(cudaMemcpyAsync(h_grids, c->d_grids_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return BC_OK;
+  }
+  if (!c->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->call_start, cudaEventDisableTiming));
+  }
+  // the copy stream must not overwrite the staging buffer while earlier work on `s` may still read it
+  CU(cudaEventRecord(c->call_start, s));
+  CU(cudaStreamWaitEvent(c->copy_stream, c->call_start, 0));
+  const size_t frame_bytes = (size_t)h * w * 3, grid_bytes = (size_t)g.Hc * g.Wc;
+  int f0 = 0;
+  for (int i = 0; i < nsub; ++i) {
+    int nb = (B - f0) / (nsub - i);
+    CU(cudaMemcpyAsync(c->d_frames_in + f0 * frame_bytes, h_bgr + f0 * frame_bytes, nb * frame_bytes,
+                       cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->copy_done[i], c->copy_stream));
+    f0 += nb;
+  }
+  f0 = 0;
+  for (int i = 0; i < nsub; ++i) {
+    int nb = (B - f0) / (nsub - i);
+    CU(cudaStreamWaitEvent(s, c->copy_done[i], 0));
+    if ((r = run_pipeline(c, c->d_frames_in + f0 * frame_bytes, h, w, nb, h_lut, w_m, h_m, cell_m, g, nullptr,
+                          c->d_grids_out + f0 * grid_bytes, s))) return r;
+    CU(cudaMemcpyAsync(h_grids + f0 * grid_bytes, c->d_grids_out + f0 * grid_bytes, nb * grid_bytes,
+                       cudaMemcpyDeviceToHost, s));
+    f0 += nb;
+  }
   CU(cudaStreamSynchronize(s));
   return BC_OK;
 }

@@ -50,9 +50,10 @@ struct UmmaSmem {
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
   static constexpr int W1_SUB = CI * 128;           // [CI out][64 in] sub-tile of the next projection
   // offsets (all multiples of 1024)
+  static constexpr int NRING = CI == 32 ? 12 : 18;  // conv-tap ring slots (TMA runs > 1 tile ahead of the MMAs)
   static constexpr int OFF_X = 0;                   // two x / y tiles (double buffered)
   static constexpr int OFF_TAPS = OFF_X + 2 * XBUF;
-  static constexpr int OFF_E2 = OFF_TAPS + 9 * TAP_BYTES;
+  static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;
   static constexpr int OFF_W = OFF_E2 + TAP_BYTES;                    // weight image starts here
   static constexpr int OFF_W2 = OFF_W;
   static constexpr int OFF_W3 = OFF_W2 + 9 * W2_TAP;
@@ -61,7 +62,7 @@ struct UmmaSmem {
   static constexpr int OFF_F = OFF_W + ((W_BYTES + 1023) / 1024) * 1024;
   static constexpr int NF = 4 * CI + 3 * C;
   static constexpr int OFF_BAR = OFF_F + ((NF * 4 + 63) / 64) * 64;
-  static constexpr int TOTAL = OFF_BAR + 128;
+  static constexpr int TOTAL = OFF_BAR + 512;
   // TMEM columns: D1 double buffered
   static constexpr uint32_t COL_D1 = 0, COL_D2 = 2 * CI, COL_D3 = 2 * CI + C;
   static constexpr uint32_t TMEM_COLS = (2 * CI + C + CI) <= 128 ? 128 : 256;
@@ -89,16 +90,17 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   float* sf = (float*)(smem + S::OFF_F);
   const float *b2 = sf, *a2 = sf + CI, *b3 = sf + 2 * CI, *a3 = b3 + C, *aout = a3 + C, *b1n = aout + C, *a1n = b1n + CI;
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
-  enum { TAP_FULL = 0, TAP_EMPTY, X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D1_EMPTY0, D1_EMPTY1,
-         E2_FULL, D2_FULL, Y_FULL, D3_FULL, W_FULL, NBARS };
+  enum { X_FULL0 = 0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D1_EMPTY0, D1_EMPTY1,
+         E2_FULL, D2_FULL, Y_FULL, D3_FULL, W_FULL, TAP_FULL, TAP_EMPTY = TAP_FULL + S::NRING, NBARS = TAP_EMPTY + S::NRING };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup: barriers, weights + parameters to smem (two bulk copies), TMEM
   if (tid == 0) {
-    const int one[] = {TAP_FULL, TAP_EMPTY, X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D2_FULL, D3_FULL, W_FULL};
+    const int one[] = {X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D2_FULL, D3_FULL, W_FULL};
     for (int b : one) mbar_init(bar(b), 1);
+    for (int i = 0; i < 2 * S::NRING; ++i) mbar_init(bar(TAP_FULL + i), 1);
     const int all[] = {D1_EMPTY0, D1_EMPTY1, E2_FULL, Y_FULL};
     for (int b : all) mbar_init(bar(b), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -121,14 +123,17 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   if (warp == 0) {
     // ============================================================ TMA producer
     if (lane == 0) {
+      uint32_t g = 0;                                   // running tap counter -> ring slot
       for (int k = 0; k < T; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         const int n = tile / p.tiles_per_frame;
         const int y0 = (tile % p.tiles_per_frame) * p.rows_per_tile;
-        if (k >= 1) mbar_wait(bar(TAP_EMPTY), (k - 1) & 1);
-        mbar_expect_tx(bar(TAP_FULL), (uint32_t)p.ntaps * S::TAP_BYTES);
-        for (int t = 0; t < p.ntaps; ++t)
-          tma_load_4d(sbase + S::OFF_TAPS + t * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(TAP_FULL));
+        for (int t = 0; t < p.ntaps; ++t, ++g) {
+          const uint32_t slot = g % S::NRING, round = g / S::NRING;
+          if (round >= 1) mbar_wait(bar(TAP_EMPTY + slot), (round - 1) & 1);
+          mbar_expect_tx(bar(TAP_FULL + slot), S::TAP_BYTES);
+          tma_load_4d(sbase + S::OFF_TAPS + slot * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(TAP_FULL + slot));
+        }
         if (full) {
           const int xb = k & 1;
           if (k >= 2) mbar_wait(bar(X_EMPTY0 + xb), ((k >> 1) - 1) & 1);
@@ -141,17 +146,20 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   } else if (warp == 1) {
     // ============================================================ MMA issuer
     if (lane == 0) {
+      uint32_t g = 0;
       auto issue_conv = [&](int k) {
         const int b = k & 1;
-        mbar_wait(bar(TAP_FULL), k & 1);
         if (k >= 2) mbar_wait(bar(D1_EMPTY0 + b), ((k >> 1) - 1) & 1);
-        tc_fence_after();
-        for (int t = 0; t < p.ntaps; ++t)
+        for (int t = 0; t < p.ntaps; ++t, ++g) {
+          const uint32_t slot = g % S::NRING, round = g / S::NRING;
+          mbar_wait(bar(TAP_FULL + slot), round & 1);
+          tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < CI / 16; ++kk)
-            umma_bf16(tmem + S::COL_D1 + b * CI, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP_BYTES + kk * 32),
+            umma_bf16(tmem + S::COL_D1 + b * CI, smem_desc<RB>(sbase + S::OFF_TAPS + slot * S::TAP_BYTES + kk * 32),
                       smem_desc<RB>(sbase + S::OFF_W2 + t * S::W2_TAP + kk * 32), IDESC_CONV, (t | kk) != 0);
-        umma_commit(bar(TAP_EMPTY));
+          umma_commit(bar(TAP_EMPTY + slot));           // slot reusable once these MMAs retire
+        }
         umma_commit(bar(D1_FULL0 + b));
       };
       mbar_wait(bar(W_FULL), 0);

@@ -87,6 +87,9 @@ int bc_set_tensor_cores(bc_ctx* ctx, int enable);
 /* 1 (default): bc_pipeline / bc_pipeline_host replay their kernel chain as one CUDA graph
  * per distinct argument set (what makes batch 1 sub-millisecond); 0: plain launches. */
 int bc_set_graphs(bc_ctx* ctx, int enable);
+/* 1 (default): bc_pipeline_host splits batches >= 32 into sub-batches whose H2D copy (internal
+ * copy stream) overlaps the previous sub-batch's kernels; 0: one copy, one pass. */
+int bc_set_host_overlap(bc_ctx* ctx, int enable);
 /* Replaces bev_transform_tools.__init__/fromJSON state (bev.py:13-41): src->dst
  * homography `h_M` (row-major 3x3, bev.py:31-32), label-map shape (rows, cols)
  * ("input image size", bev.py:30,169), warped size (ww, wh) ("output image size",
