@@ -50,7 +50,7 @@ struct UmmaSmem {
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
   static constexpr int W1_SUB = CI * 128;           // [CI out][64 in] sub-tile of the next projection
   // offsets (all multiples of 1024)
-  static constexpr int NRING = CI == 32 ? 12 : 18;  // conv-tap ring slots (TMA runs > 1 tile ahead of the MMAs)
+  static constexpr int NRING = CI == 32 ? 12 : 9;  // conv-tap ring slots (TMA runs > 1 tile ahead of the MMAs)
   static constexpr int OFF_X = 0;                   // two x / y tiles (double buffered)
   static constexpr int OFF_TAPS = OFF_X + 2 * XBUF;
   static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;
@@ -76,7 +76,7 @@ struct UmmaSmem {
 //   warps 2-5 epilogue       one TMEM lane (= pixel) per thread: D1 -> e2 (smem), D2 + x -> y (smem,
 //                            TMA store), D3 -> e1' (global)
 template <int C, int CI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (C == 64 ? 2 : 1))
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
@@ -450,7 +450,8 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  int ctas = num_sms * (C == 64 ? 2 : 1);
+  int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   k_umma_bottleneck<C, CI><<<grid, 192, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }
