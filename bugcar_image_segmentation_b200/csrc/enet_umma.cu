@@ -20,6 +20,7 @@
 // reference executes (models.py:43-44); semantics in oracle/enet_oracle.py `regular`.
 #include "umma_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -39,50 +40,82 @@ struct UmmaParams {
   const float* fparams; // b2[CI] a2[CI] b3[C] a3[C] aout[C] b1n[CI] a1n[CI]
 };
 
+// weight image (identical in global and shared memory): offsets relative to its start
 template <int C, int CI>
-struct UmmaSmem {
+struct UmmaWeights {
   static constexpr int RB = CI * 2;                 // row bytes of the CI-wide operands (64 / 32)
-  static constexpr int TAP_BYTES = 128 * RB;        // one A tap tile
   static constexpr int W2_TAP = CI * RB;            // one tap of W2: [CI out][CI in]
   static constexpr int W3_BYTES = C * RB;           // [C out][CI in]
+  static constexpr int NSUB = C / 64;
+  static constexpr int W1_SUB = CI * 128;           // [CI out][64 in] sub-tile of the next projection
+  static constexpr int OFF_W2 = 0;
+  static constexpr int OFF_W3 = 9 * W2_TAP;
+  static constexpr int OFF_W1 = ((9 * W2_TAP + W3_BYTES + 1023) / 1024) * 1024;   // 128-byte swizzle: 1 KB aligned
+  static constexpr int W_BYTES = OFF_W1 + NSUB * W1_SUB;
+  static constexpr int NF = 4 * CI + 3 * C;         // fp32 parameter block
+};
+
+// NG = epilogue groups per CTA (tiles in flight), MINB = CTAs per SM
+template <int C, int CI, int NG_, int MINB_>
+struct UmmaSmem {
+  using Wt = UmmaWeights<C, CI>;
+  static constexpr int NG = NG_, MINB = MINB_;
+  static constexpr int THREADS = 128 + 128 * NG;
+  static constexpr int RB = CI * 2;
+  static constexpr int TAP_BYTES = 128 * RB;        // one A tap tile
   static constexpr int XSUB = 128 * 128;            // one 64-channel sub-tile of x / y
   static constexpr int NSUB = C / 64;
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
-  static constexpr int W1_SUB = CI * 128;           // [CI out][64 in] sub-tile of the next projection
+  static constexpr int NX = NG + 1;                 // x / y tile ring (one tile of prefetch)
+  static constexpr int NRING = (MINB == 1 && CI == 16) ? 18 : 9;   // conv-tap ring slots
   // offsets (all multiples of 1024)
-  static constexpr int NRING = CI == 32 ? 12 : 9;  // conv-tap ring slots (TMA runs > 1 tile ahead of the MMAs)
-  static constexpr int OFF_X = 0;                   // two x / y tiles (double buffered)
-  static constexpr int OFF_TAPS = OFF_X + 2 * XBUF;
-  static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;
-  static constexpr int OFF_W = OFF_E2 + TAP_BYTES;                    // weight image starts here
-  static constexpr int OFF_W2 = OFF_W;
-  static constexpr int OFF_W3 = OFF_W2 + 9 * W2_TAP;
-  static constexpr int OFF_W1 = OFF_W + ((9 * W2_TAP + W3_BYTES + 1023) / 1024) * 1024;   // 128-byte swizzle: 1 KB aligned
-  static constexpr int W_BYTES = OFF_W1 - OFF_W + NSUB * W1_SUB;
-  static constexpr int OFF_F = OFF_W + ((W_BYTES + 1023) / 1024) * 1024;
-  static constexpr int NF = 4 * CI + 3 * C;
-  static constexpr int OFF_BAR = OFF_F + ((NF * 4 + 63) / 64) * 64;
-  static constexpr int TOTAL = OFF_BAR + 512;
-  // TMEM columns: D1 double buffered
-  static constexpr uint32_t COL_D1 = 0, COL_D2 = 2 * CI, COL_D3 = 2 * CI + C;
-  static constexpr uint32_t TMEM_COLS = (2 * CI + C + CI) <= 128 ? 128 : 256;
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_TAPS = OFF_X + NX * XBUF;
+  static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;         // one e2 tile per group
+  static constexpr int OFF_W = OFF_E2 + NG * TAP_BYTES;               // weight image starts here
+  static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
+  static constexpr int OFF_F = OFF_W + ((Wt::W_BYTES + 1023) / 1024) * 1024;
+  static constexpr int OFF_BAR = OFF_F + ((Wt::NF * 4 + 63) / 64) * 64;
+  static constexpr int TOTAL = OFF_BAR + 1024;
+  // barriers
+  static constexpr int X_FULL = 0, D1_FULL = X_FULL + NX, D1_EMPTY = D1_FULL + NG,
+                       E2_FULL = D1_EMPTY + NG, D2_FULL = E2_FULL + NG, Y_FULL = D2_FULL + NG, D3_FULL = Y_FULL + NG,
+                       W_FULL = D3_FULL + NG, TAP_FULL = W_FULL + 1, TAP_EMPTY = TAP_FULL + NRING,
+                       NBARS = TAP_EMPTY + NRING;
+  static_assert(NBARS * 8 + 8 <= 1024, "barrier block");
+  // 227 KB per CTA, 228 KB per SM with 1 KB reserved per resident CTA; + 1 KB alignment slack
+  static_assert(TOTAL + 1024 <= 232448 && (TOTAL + 2048) * MINB <= 233472, "shared memory budget");
+  // TMEM columns: every group owns a D1 / D2 / D3 accumulator
+  static constexpr uint32_t COL_D1 = 0, COL_D2 = NG * CI, COL_D3 = NG * (CI + C);
+  static constexpr uint32_t COLS_USED = NG * (2 * CI + C);
+  static constexpr uint32_t TMEM_COLS = COLS_USED <= 32 ? 32 : COLS_USED <= 64 ? 64 : COLS_USED <= 128 ? 128
+                                        : COLS_USED <= 256 ? 256 : 512;
+  static_assert(COLS_USED <= 512 && TMEM_COLS * MINB <= 512, "TMEM budget");
 };
 
-
-// Warp-specialised persistent kernel, 192 threads:
-//   warp 0    TMA producer   conv taps of tile k+1 as soon as the conv MMAs of tile k retire;
-//                            residual tile x double buffered
-//   warp 1    MMA issuer     conv(k) -> expansion(k) -> conv(k+1) -> projection(k); D1 double buffered
-//   warps 2-5 epilogue       one TMEM lane (= pixel) per thread: D1 -> e2 (smem), D2 + x -> y (smem,
-//                            TMA store), D3 -> e1' (global)
-template <int C, int CI>
-__global__ void __launch_bounds__(192, (C == 64 ? 2 : 1))
+// Warp-specialised persistent kernel, 128 + 128 * NG threads.  A CTA keeps NG tiles in flight:
+// tile k of the CTA belongs to epilogue group k % NG, which owns a D1/D2/D3 accumulator and an
+// e2 tile, so the serial chain of one tile (conv MMA -> epilogue 1 -> expansion MMA -> epilogue
+// 2 -> projection MMA -> epilogue 3) overlaps with the chains of the other groups.  Every
+// service thread blocks on exactly one barrier sequence (a thread that polls several barriers
+// turned out to be the bottleneck: ~200 cycles per probe).
+//   warp 0    TMA producer   conv taps through a ring of NRING slots (+ the first residual tiles)
+//   warp 1    MMA issuer     conv taps      -> D1[group]
+//   warp 2    MMA issuer     expansion      -> D2[group]
+//   warp 3    MMA issuer     next projection-> D3[group]
+//   warps 4.. epilogue       group g = (warp - 4) / 4; one TMEM lane (= pixel) per thread:
+//                            D1 -> e2 (smem), D2 + x -> y (smem, TMA store), D3 -> e1' (global);
+//                            its first thread stores y and requests the x tile that reuses the buffer
+template <int C, int CI, int NG, int MINB>
+__global__ void __launch_bounds__(128 + 128 * NG, MINB)
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
                   const UmmaParams p) {
-  using S = UmmaSmem<C, CI>;
+  using S = UmmaSmem<C, CI, NG, MINB>;
+  using Wt = UmmaWeights<C, CI>;
   constexpr int RB = S::RB;
+  constexpr int NX = S::NX;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: align by hand (1 KB slack requested)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -90,23 +123,22 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   float* sf = (float*)(smem + S::OFF_F);
   const float *b2 = sf, *a2 = sf + CI, *b3 = sf + 2 * CI, *a3 = b3 + C, *aout = a3 + C, *b1n = aout + C, *a1n = b1n + CI;
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
-  enum { X_FULL0 = 0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D1_EMPTY0, D1_EMPTY1,
-         E2_FULL, D2_FULL, Y_FULL, D3_FULL, W_FULL, TAP_FULL, TAP_EMPTY = TAP_FULL + S::NRING, NBARS = TAP_EMPTY + S::NRING };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
-  uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
+  uint32_t* tmem_slot = (uint32_t*)&bars[S::NBARS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup: barriers, weights + parameters to smem (two bulk copies), TMEM
   if (tid == 0) {
-    const int one[] = {X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, D1_FULL0, D1_FULL1, D2_FULL, D3_FULL, W_FULL};
-    for (int b : one) mbar_init(bar(b), 1);
-    for (int i = 0; i < 2 * S::NRING; ++i) mbar_init(bar(TAP_FULL + i), 1);
-    const int all[] = {D1_EMPTY0, D1_EMPTY1, E2_FULL, Y_FULL};
-    for (int b : all) mbar_init(bar(b), 128);
+    for (int i = 0; i < S::NBARS; ++i) {
+      // D1_EMPTY / E2_FULL / Y_FULL: every thread of the group arrives; the rest: one arrival
+      const bool by_group = (i >= S::D1_EMPTY && i < S::D1_EMPTY + NG) || (i >= S::E2_FULL && i < S::E2_FULL + NG) ||
+                            (i >= S::Y_FULL && i < S::Y_FULL + NG);
+      mbar_init(bar(i), by_group ? 128 : 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar(W_FULL), S::W_BYTES + S::NF * 4);
-    bulk_load(sbase + S::OFF_W, p.wblob, S::W_BYTES, bar(W_FULL));
-    bulk_load(sbase + S::OFF_F, p.fparams, S::NF * 4, bar(W_FULL));
+    mbar_expect_tx(bar(S::W_FULL), Wt::W_BYTES + Wt::NF * 4);
+    bulk_load(sbase + S::OFF_W, p.wblob, Wt::W_BYTES, bar(S::W_FULL));
+    bulk_load(sbase + S::OFF_F, p.fparams, Wt::NF * 4, bar(S::W_FULL));
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
@@ -121,90 +153,100 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   const bool full = !p.conv_only;
 
   if (warp == 0) {
-    // ============================================================ TMA producer
+    // ============================================================ TMA producer (conv taps)
     if (lane == 0) {
-      uint32_t g = 0;                                   // running tap counter -> ring slot
+      if (full)                                          // first NX residual tiles; the rest are
+        for (int k = 0; k < T && k < NX; ++k) {          // requested by the thread that frees a buffer
+          const int tile = blockIdx.x + k * gridDim.x;
+          mbar_expect_tx(bar(S::X_FULL + k), S::XBUF);
+          for (int s = 0; s < S::NSUB; ++s)
+            tma_load_2d(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k));
+        }
+      int slot = 0, round = 0;
       for (int k = 0; k < T; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         const int n = tile / p.tiles_per_frame;
         const int y0 = (tile % p.tiles_per_frame) * p.rows_per_tile;
-        for (int t = 0; t < p.ntaps; ++t, ++g) {
-          const uint32_t slot = g % S::NRING, round = g / S::NRING;
-          if (round >= 1) mbar_wait(bar(TAP_EMPTY + slot), (round - 1) & 1);
-          mbar_expect_tx(bar(TAP_FULL + slot), S::TAP_BYTES);
-          tma_load_4d(sbase + S::OFF_TAPS + slot * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(TAP_FULL + slot));
-        }
-        if (full) {
-          const int xb = k & 1;
-          if (k >= 2) mbar_wait(bar(X_EMPTY0 + xb), ((k >> 1) - 1) & 1);
-          mbar_expect_tx(bar(X_FULL0 + xb), S::XBUF);
-          for (int s = 0; s < S::NSUB; ++s)
-            tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + xb));
+        for (int t = 0; t < p.ntaps; ++t) {
+          if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
+          mbar_expect_tx(bar(S::TAP_FULL + slot), S::TAP_BYTES);
+          tma_load_4d(sbase + S::OFF_TAPS + slot * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
+          if (++slot == S::NRING) { slot = 0; ++round; }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer
+    // ============================================================ MMA issuer: conv taps -> D1[group]
     if (lane == 0) {
-      uint32_t g = 0;
-      auto issue_conv = [&](int k) {
-        const int b = k & 1;
-        if (k >= 2) mbar_wait(bar(D1_EMPTY0 + b), ((k >> 1) - 1) & 1);
-        for (int t = 0; t < p.ntaps; ++t, ++g) {
-          const uint32_t slot = g % S::NRING, round = g / S::NRING;
-          mbar_wait(bar(TAP_FULL + slot), round & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < CI / 16; ++kk)
-            umma_bf16(tmem + S::COL_D1 + b * CI, smem_desc<RB>(sbase + S::OFF_TAPS + slot * S::TAP_BYTES + kk * 32),
-                      smem_desc<RB>(sbase + S::OFF_W2 + t * S::W2_TAP + kk * 32), IDESC_CONV, (t | kk) != 0);
-          umma_commit(bar(TAP_EMPTY + slot));           // slot reusable once these MMAs retire
-        }
-        umma_commit(bar(D1_FULL0 + b));
-      };
-      mbar_wait(bar(W_FULL), 0);
-      if (T > 0) issue_conv(0);
+      int slot = 0, round = 0;
+      mbar_wait(bar(S::W_FULL), 0);
       for (int k = 0; k < T; ++k) {
-        if (full) {
-          mbar_wait(bar(E2_FULL), k & 1);
+        const int g = k % NG;
+        if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+        for (int t = 0; t < p.ntaps; ++t) {
+          mbar_wait(bar(S::TAP_FULL + slot), round & 1);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < CI / 16; ++kk)
-            umma_bf16(tmem + S::COL_D2, smem_desc<RB>(sbase + S::OFF_E2 + kk * 32),
-                      smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), IDESC_EXP, kk != 0);
-          umma_commit(bar(D2_FULL));
+            umma_bf16(tmem + S::COL_D1 + g * CI, smem_desc<RB>(sbase + S::OFF_TAPS + slot * S::TAP_BYTES + kk * 32),
+                      smem_desc<RB>(sbase + S::OFF_W2 + t * Wt::W2_TAP + kk * 32), IDESC_CONV, (t | kk) != 0);
+          umma_commit(bar(S::TAP_EMPTY + slot));        // slot reusable once these MMAs retire
+          if (++slot == S::NRING) { slot = 0; ++round; }
         }
-        if (k + 1 < T) issue_conv(k + 1);
-        if (full && p.has_next) {
-          const uint32_t xs = sbase + S::OFF_X + (k & 1) * S::XBUF;
-          mbar_wait(bar(Y_FULL), k & 1);
-          tc_fence_after();
+        umma_commit(bar(S::D1_FULL + g));
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ MMA issuer: expansion e2 -> D2[group]
+    if (lane == 0 && full) {
+      mbar_wait(bar(S::W_FULL), 0);
+      for (int k = 0; k < T; ++k) {
+        const int g = k % NG;
+        mbar_wait(bar(S::E2_FULL + g), (k / NG) & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < C / 16; ++kk)
-            umma_bf16(tmem + S::COL_D3, smem_desc<128>(xs + (kk / 4) * S::XSUB + (kk % 4) * 32),
-                      smem_desc<128>(sbase + S::OFF_W1 + (kk / 4) * S::W1_SUB + (kk % 4) * 32), IDESC_PROJ, kk != 0);
-          umma_commit(bar(D3_FULL));
-        }
+        for (int kk = 0; kk < CI / 16; ++kk)
+          umma_bf16(tmem + S::COL_D2 + g * C, smem_desc<RB>(sbase + S::OFF_E2 + g * S::TAP_BYTES + kk * 32),
+                    smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), IDESC_EXP, kk != 0);
+        umma_commit(bar(S::D2_FULL + g));
+      }
+    }
+  } else if (warp == 3) {
+    // ============================================================ MMA issuer: next projection y -> D3[group]
+    if (lane == 0 && full && p.has_next) {
+      mbar_wait(bar(S::W_FULL), 0);
+      for (int k = 0; k < T; ++k) {
+        const int g = k % NG;
+        const uint32_t xs = sbase + S::OFF_X + (k % NX) * S::XBUF;
+        mbar_wait(bar(S::Y_FULL + g), (k / NG) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < C / 16; ++kk)
+          umma_bf16(tmem + S::COL_D3 + g * CI, smem_desc<128>(xs + (kk / 4) * S::XSUB + (kk % 4) * 32),
+                    smem_desc<128>(sbase + S::OFF_W1 + (kk / 4) * Wt::W1_SUB + (kk % 4) * 32), IDESC_PROJ, kk != 0);
+        umma_commit(bar(S::D3_FULL + g));
       }
     }
   } else {
-    // ============================================================ epilogue (warps 2..5)
+    // ============================================================ epilogue (warps 4..)
+    const int grp = (warp - 4) >> 2;         // epilogue group = tile slot
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;             // row of the tile = pixel = TMEM lane
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const bool storer = (warp == 2 && lane == 0);
-    mbar_wait(bar(W_FULL), 0);
-    for (int k = 0; k < T; ++k) {
+    const bool storer = ((warp & 3) == 0 && lane == 0);
+    uint8_t* e2buf = smem + S::OFF_E2 + grp * S::TAP_BYTES;
+    mbar_wait(bar(S::W_FULL), 0);
+    for (int k = grp; k < T; k += NG) {
       const int tile = blockIdx.x + k * gridDim.x;
-      const int b = k & 1;
+      const uint32_t par = (uint32_t)(k / NG) & 1;
       // ---- epilogue 1: +bias, PReLU, bf16 -> e2 tile (A operand of the expansion) or global
       {
         float v[CI];
-        mbar_wait(bar(D1_FULL0 + b), (k >> 1) & 1);
+        mbar_wait(bar(S::D1_FULL + grp), par);
         tc_fence_after();
-        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D1 + b * CI, v); else tmem_ld16(tm_lane + S::COL_D1 + b * CI, v);
+        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D1 + grp * CI, v); else tmem_ld16(tm_lane + S::COL_D1 + grp * CI, v);
         tc_fence_before();
-        mbar_arrive(bar(D1_EMPTY0 + b));
+        mbar_arrive(bar(S::D1_EMPTY + grp));
 #pragma unroll
         for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b2[j], a2[j]);
         if (!full) {
@@ -217,21 +259,22 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         }
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
-          *reinterpret_cast<uint4*>(smem + S::OFF_E2 + swz<RB>(m * RB + c * 16)) =
+          *reinterpret_cast<uint4*>(e2buf + swz<RB>(m * RB + c * 16)) =
               make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
                          pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
         fence_proxy_async();
-        mbar_arrive(bar(E2_FULL));
+        mbar_arrive(bar(S::E2_FULL + grp));
       }
       // ---- epilogue 2: +bias, PReLU, + residual, PReLU, bf16 -> y tile (in place over x)
-      uint8_t* xt = smem + S::OFF_X + b * S::XBUF;
-      mbar_wait(bar(X_FULL0 + b), (k >> 1) & 1);
-      mbar_wait(bar(D2_FULL), k & 1);
+      const int xb = k % NX;
+      uint8_t* xt = smem + S::OFF_X + xb * S::XBUF;
+      mbar_wait(bar(S::X_FULL + xb), (uint32_t)(k / NX) & 1);
+      mbar_wait(bar(S::D2_FULL + grp), par);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
-        tmem_ld32(tm_lane + S::COL_D2 + c0, v);
+        tmem_ld32(tm_lane + S::COL_D2 + grp * C + c0, v);
         uint8_t* xrow = xt + (c0 / 64) * S::XSUB;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 channels
@@ -252,20 +295,20 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(bar(Y_FULL));
+      mbar_arrive(bar(S::Y_FULL + grp));
       // ---- y tile -> global (TMA store by one thread once every row is written)
       if (storer) {
-        mbar_wait(bar(Y_FULL), k & 1);
+        mbar_wait(bar(S::Y_FULL + grp), par);
         for (int s = 0; s < S::NSUB; ++s)
-          tma_store_2d(&map_y, sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, s * 64, tile * 128);
+          tma_store_2d(&map_y, sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, s * 64, tile * 128);
         tma_store_commit();
       }
       // ---- epilogue 3: the next block's projection: +bias, PReLU, bf16 -> e1' (global)
       if (p.has_next) {
-        mbar_wait(bar(D3_FULL), k & 1);
+        mbar_wait(bar(S::D3_FULL + grp), par);
         tc_fence_after();
         float v[CI];
-        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D3, v); else tmem_ld16(tm_lane + S::COL_D3, v);
+        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D3 + grp * CI, v); else tmem_ld16(tm_lane + S::COL_D3 + grp * CI, v);
         tc_fence_before();
 #pragma unroll
         for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
@@ -277,9 +320,15 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       }
       // the x/y buffer may be reloaded once the store has read it (and the projection MMAs,
       // which the D3_FULL wait above covers, have consumed it)
+      // ... and this thread, which knows it first, requests the tile that uses the buffer next
       if (storer) {
         tma_store_wait_read();
-        mbar_arrive(bar(X_EMPTY0 + b));
+        if (k + NX < T) {
+          const int nt = blockIdx.x + (k + NX) * gridDim.x;
+          mbar_expect_tx(bar(S::X_FULL + xb), S::XBUF);
+          for (int s = 0; s < S::NSUB; ++s)
+            tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb));
+        }
       }
     }
     if (storer) tma_store_wait_all();
@@ -379,18 +428,18 @@ template <int C, int CI>
 static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* conv_b, const float* conv_a,
                     const float* exp_w, const float* exp_b, const float* exp_a, const float* alpha_out,
                     const float* next_w, const float* next_b, const float* next_a) {
-  using S = UmmaSmem<C, CI>;
+  using S = UmmaWeights<C, CI>;
   std::vector<uint8_t> img(S::W_BYTES, 0);
   std::vector<float> cw(conv_w, conv_w + (size_t)ntaps * CI * CI);
-  for (int t = 0; t < ntaps; ++t) pack_rows(img.data() + (S::OFF_W2 - S::OFF_W) + t * S::W2_TAP, CI, S::RB, cw, CI, CI, t, 0);
+  for (int t = 0; t < ntaps; ++t) pack_rows(img.data() + S::OFF_W2 + t * S::W2_TAP, CI, S::RB, cw, CI, CI, t, 0);
   if (exp_w) {
     std::vector<float> ew(exp_w, exp_w + (size_t)CI * C);
-    pack_rows(img.data() + (S::OFF_W3 - S::OFF_W), C, S::RB, ew, CI, C, 0, 0);
+    pack_rows(img.data() + S::OFF_W3, C, S::RB, ew, CI, C, 0, 0);
   }
   if (next_w) {
     std::vector<float> nw(next_w, next_w + (size_t)C * CI);
     for (int s = 0; s < S::NSUB; ++s)
-      pack_rows(img.data() + (S::OFF_W1 - S::OFF_W) + s * S::W1_SUB, CI, 128, nw, C, CI, 0, s * 64);
+      pack_rows(img.data() + S::OFF_W1 + s * S::W1_SUB, CI, 128, nw, C, CI, 0, s * 64);
   }
   std::vector<float> f(S::NF, 0.f);
   float* b2 = f.data(); float* a2 = b2 + CI; float* b3 = a2 + CI; float* a3 = b3 + C; float* ao = a3 + C;
@@ -422,10 +471,10 @@ void umma_free(UmmaPack& p) {
   p = UmmaPack();
 }
 
-template <int C, int CI>
+template <int C, int CI, int NG, int MINB>
 static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
-  using S = UmmaSmem<C, CI>;
+  using S = UmmaSmem<C, CI, NG, MINB>;
   CUtensorMap me1, mx, my;
   if (!make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
@@ -446,23 +495,40 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   static bool attr_done = false;
   const int smem = S::TOTAL + 1024;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI, NG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  int ctas = num_sms * (C == 64 ? 2 : 1);
+  const int ctas = num_sms * MINB;
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  k_umma_bottleneck<C, CI><<<grid, 192, smem, s>>>(me1, mx, my, p);
+  k_umma_bottleneck<C, CI, NG, MINB><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
+}
+
+// Tiles in flight per SM = epilogue groups per CTA x CTAs per SM.  Tuning knobs (measured on
+// B200): BC_UMMA_CFG64 / BC_UMMA_CFG128 = "<groups><ctas>", e.g. "22".
+static int cfg_from_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && v[0] >= '1' && v[0] <= '4' && v[1] >= '1' && v[1] <= '2' && !v[2]) ? (v[0] - '0') * 10 + (v[1] - '0') : dflt;
 }
 
 cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H, int W,
                         const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
   if (128 % W != 0 && W % 128 != 0) return cudaErrorInvalidValue;
-  if (pk.C == 128 && pk.CI == 32)
-    return launch_one<128, 32>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s);
-  if (pk.C == 64 && pk.CI == 16)
-    return launch_one<64, 16>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s);
+  static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 22), cfg128 = cfg_from_env("BC_UMMA_CFG128", 21);
+#define BC_LAUNCH(C_, CI_, NG_, MB_) \
+  return launch_one<C_, CI_, NG_, MB_>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s)
+  if (pk.C == 128 && pk.CI == 32) {
+    if (cfg128 == 11) BC_LAUNCH(128, 32, 1, 1);
+    BC_LAUNCH(128, 32, 2, 1);
+  }
+  if (pk.C == 64 && pk.CI == 16) {
+    if (cfg64 == 12) BC_LAUNCH(64, 16, 1, 2);
+    if (cfg64 == 41) BC_LAUNCH(64, 16, 4, 1);
+    if (cfg64 == 31) BC_LAUNCH(64, 16, 3, 1);
+    BC_LAUNCH(64, 16, 2, 2);
+  }
+#undef BC_LAUNCH
   return cudaErrorInvalidValue;
 }
 
