@@ -120,6 +120,8 @@ struct bc_ctx {
 
   // ---- resize tables, keyed by source size
   std::map<std::pair<int, int>, ResizeTab> resize_tabs;
+  // ---- K9 coordinate tables, keyed by the geometry (cleared by bc_set_bev)
+  std::vector<std::pair<BevGeom, uint2*>> occ_tables;
 
   // ---- multi-GPU gather
   int8_t* gather_base = nullptr;
@@ -760,7 +762,17 @@ void invert3x3(const double* a, double* t) {
 }
 
 // bev.py:172-176, 183-190 (float -> int() truncations; Python float == C double)
-int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int ros, BevGeom& g) {
+void free_occ_tables(bc_ctx* c) {
+  for (auto& kv : c->occ_tables) cudaFree(kv.second);
+  c->occ_tables.clear();
+}
+
+// Geometry of one grid request; with `table` also the (cached) device table of K9's
+// frame-independent coordinates.  May allocate and synchronise on first use of a geometry,
+// so it runs before any graph capture.
+int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int ros, BevGeom& g,
+              bool with_table = true) {
+  memset(&g, 0, sizeof g);                // the struct doubles as a cache key (padding included)
   if (!c->bev_set) return fail(c, BC_ERR_STATE, "bc_set_bev has not been called");
   if (!(cell_m > 0.0) || !(w_m > 0.0) || !(h_m > 0.0)) return fail(c, BC_ERR_ARG, "grid extents and cell size must be positive");
   double cell_px = cell_m * 100 / c->cm_per_px;
@@ -786,6 +798,20 @@ int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int 
   // cv::resize INTER_NEAREST: sx = min(floor(dx * (1 / (dst / src))), src - 1) in fp64
   g.ifx = 1.0 / ((double)Wc / (double)occ_w_px);
   g.ify = 1.0 / ((double)Hc / (double)occ_h_px);
+  if (!with_table) return BC_OK;
+  BevGeom key = g;
+  key.binary = key.ros_layout = 0;        // the coordinates do not depend on them
+  for (auto& kv : c->occ_tables)
+    if (memcmp(&kv.first, &key, sizeof key) == 0) { g.table = kv.second; return BC_OK; }
+  CU(cudaSetDevice(c->device));
+  uint2* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)25 * Hc * Wc * sizeof(uint2)));
+  launch_occ_table(key, d, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(d); return fail(c, BC_ERR_CUDA, std::string("occupancy table: ") + cudaGetErrorString(e)); }
+  if (c->occ_tables.size() >= 8) { cudaFree(c->occ_tables.front().second); c->occ_tables.erase(c->occ_tables.begin()); }
+  c->occ_tables.emplace_back(key, d);
+  g.table = d;
   return BC_OK;
 }
 
@@ -926,6 +952,7 @@ void bc_destroy(bc_ctx* c) {
   free_net(c);
   free_scratch(c);
   for (auto& kv : c->resize_tabs) if (kv.second.blob) cudaFree(kv.second.blob);
+  free_occ_tables(c);
   for (auto& r : c->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1001,6 +1028,7 @@ int bc_set_bev(bc_ctx* c, const double h_M[9], int in_rows, int in_cols, int war
   CU(cudaSetDevice(c->device));
   CU(cudaDeviceSynchronize());
   invalidate_graphs(c);
+  free_occ_tables(c);
   memcpy(c->M, h_M, sizeof c->M);
   invert3x3(c->M, c->Mi);
   c->in_rows = in_rows; c->in_cols = in_cols;
@@ -1091,7 +1119,7 @@ int bc_argmax_lut(bc_ctx* c, const float* d_logits, int B, int C, int H, int W, 
 int bc_occgrid_shape(bc_ctx* c, double w_m, double h_m, double cell_m, int* Hc, int* Wc) {
   if (!c) return BC_ERR_ARG;
   BevGeom g;
-  int r = make_geom(c, w_m, h_m, cell_m, 0, 0, g);
+  int r = make_geom(c, w_m, h_m, cell_m, 0, 0, g, false);
   if (r) return r;
   if (Hc) *Hc = g.Hc;
   if (Wc) *Wc = g.Wc;

@@ -3,7 +3,9 @@
 //   K1  k_resize        cv2.resize(bgr,(512,256)) bit-exact            models.py:87
 //       k_preprocess    BGR->RGB, (u/256-mean)/std, HWC->CHW           models.py:89-94
 //   K8' k_argmax_lut    tf.math.argmax(axis=1) + class LUT             models.py:55-58,67 / 78-81
-//   K9  k_occgrid       warpPerspective + crop/paste + 3x3 open + nearest resize + int8 map,
+//   K9  k_occ_table     per calibration: nearest-resize + crop/paste + warpPerspective
+//                       coordinates of every grid cell's 5x5 template neighbourhood
+//       k_occgrid       per frame: bilinear label blend + 3x3 open + int8 map,
 //                       one kernel, no intermediate image              bev.py:166-246 / 97-144
 //
 // All of it is byte/integer arithmetic with fp64 coordinates, bound by HBM/L2 traffic
@@ -114,12 +116,22 @@ void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lu
 }
 
 // ------------------------------------------------------------------------------ K9
-// Value of the warped (label+1) image at destination pixel (x, y): OpenCV's
-// warpPerspective, INTER_LINEAR, BORDER_CONSTANT 0, 5-bit fixed-point weights.  The
-// fp64 association (block origin xb) and the absence of FMA contraction reproduce
-// WarpPerspectiveInvoker exactly (oracle/cv_ops.py warp_coords_fixed).
-__device__ __forceinline__ int warp_sample(const uint8_t* __restrict__ lab, const BevGeom& g,
-                                           int x, int y) {
+// The geometry of K9 does not depend on the frame: which template pixel a grid cell takes,
+// which 5x5 template pixels the 3x3 opening looks at, and where each of those falls in the
+// label map are functions of the calibration only.  k_occ_table evaluates them ONCE per
+// (calibration, grid request) into a table; the per-frame kernel is then a pure integer
+// gather + blend + bit logic on the label bytes.
+//
+// Table entry (8 bytes) for cell `c`, neighbourhood position `pos = j*5+i` (template pixel
+// (ty-2+j, tx-2+i)), stored [pos][cell] so that a warp reads it coalesced:
+//   .x = sx (int16) | sy (int16) << 16      top-left source pixel of the bilinear footprint
+//   .y = ax | ay << 8 | flags << 16         5-bit fractions; flag 1 = inside the template,
+//                                           flag 2 = inside the pasted crop (else the value is 0)
+
+// Fixed-point source coordinates of warped pixel (x, y): OpenCV's warpPerspective,
+// INTER_LINEAR, 5-bit fractions.  The fp64 association (block origin xb) and the absence of
+// FMA contraction reproduce WarpPerspectiveInvoker exactly (oracle/cv_ops.py warp_coords_fixed).
+__device__ __forceinline__ void warp_coords(const BevGeom& g, int x, int y, int& X, int& Y) {
   int xb = (x / g.bw0) * g.bw0;
   double dxb = (double)xb, dx1 = (double)(x - xb), dy = (double)y;
   double X0 = __dadd_rn(__dadd_rn(__dmul_rn(g.Mi[0], dxb), __dmul_rn(g.Mi[1], dy)), g.Mi[2]);
@@ -131,13 +143,52 @@ __device__ __forceinline__ int warp_sample(const uint8_t* __restrict__ lab, cons
   double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(g.Mi[3], dx1)), W);
   fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
   fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
-  int X = __double2int_rn(fX);      // cvRound: round half to even
-  int Y = __double2int_rn(fY);
-  int sx = min(max(X >> 5, -32768), 32767);   // saturate_cast<short>
-  int sy = min(max(Y >> 5, -32768), 32767);
-  int ax = X & 31, ay = Y & 31;
+  X = __double2int_rn(fX);      // cvRound: round half to even
+  Y = __double2int_rn(fY);
+}
+
+__global__ void __launch_bounds__(128)
+k_occ_table(const BevGeom g, uint2* __restrict__ table) {
+  const int cells = g.Hc * g.Wc;
+  int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  int pos = blockIdx.y;
+  if (cell >= cells) return;
+  int cx = cell % g.Wc, cy = cell / g.Wc;
+  // cv::resize INTER_NEAREST (bev.py:209-212): min(floor(d * ifx), src - 1) in fp64
+  int tx = min((int)floor(__dmul_rn((double)cx, g.ifx)), g.occ_w_px - 1);
+  int ty = min((int)floor(__dmul_rn((double)cy, g.ify)), g.occ_h_px - 1);
+  int x = tx - 2 + pos % 5, y = ty - 2 + pos / 5;
+  uint2 e = make_uint2(0u, 0u);
+  if (x >= 0 && x < g.occ_w_px && y >= 0 && y < g.occ_h_px) {
+    unsigned flags = 1;
+    // crop of the warped image pasted into a zero template (bev.py:183-195)
+    int px = x - g.gl, py = y - g.gt;
+    if (px >= 0 && py >= 0 && px < g.crop_w && py < g.crop_h) {
+      int X, Y;
+      warp_coords(g, px + g.wl, py + g.wt, X, Y);
+      int sx = min(max(X >> 5, -32768), 32767);   // saturate_cast<short>
+      int sy = min(max(Y >> 5, -32768), 32767);
+      e.x = (unsigned)(sx & 0xffff) | ((unsigned)(sy & 0xffff) << 16);
+      e.y = (unsigned)(X & 31) | ((unsigned)(Y & 31) << 8);
+      flags |= 2;
+    }
+    e.y |= flags << 16;
+  }
+  table[(size_t)pos * cells + cell] = e;
+}
+
+void launch_occ_table(const BevGeom& g, uint2* table, cudaStream_t s) {
+  dim3 grid((g.Hc * g.Wc + 127) / 128, 25);
+  k_occ_table<<<grid, 128, 0, s>>>(g, table);
+}
+
+// (labels + 1) blended at the table entry's footprint: (sum p * wy * wx + 512) >> 10, taps
+// outside the label map contribute 0 (BORDER_CONSTANT), np.add(segmap, 1) wraps in uint8.
+__device__ __forceinline__ int occ_sample(const uint8_t* __restrict__ lab, uint2 e, int rows, int cols) {
+  if (!(e.y & (2u << 16))) return 0;
+  int sx = (int)(short)(e.x & 0xffff), sy = (int)(short)(e.x >> 16);
+  int ax = e.y & 31, ay = (e.y >> 8) & 31;
   int acc = 0;
-  const int rows = g.in_rows, cols = g.in_cols;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     int yy = sy + j;
@@ -155,83 +206,80 @@ __device__ __forceinline__ int warp_sample(const uint8_t* __restrict__ lab, cons
   return (acc + 512) >> 10;
 }
 
-// template pixel (ty, tx): crop of the warped image pasted into a zero image
-// (bev.py:183-195)
-__device__ __forceinline__ int template_px(const uint8_t* __restrict__ lab, const BevGeom& g,
-                                           int tx, int ty) {
-  int cx = tx - g.gl, cy = ty - g.gt;
-  if (cx < 0 || cy < 0 || cx >= g.crop_w || cy >= g.crop_h) return 0;
-  return warp_sample(lab, g, cx + g.wl, cy + g.wt);
-}
-
 __device__ __forceinline__ bool is_occ(int v, int binary) {
   return binary ? (v == 1) : (v == 1 || v == 3);   // bev.py:128 / bev.py:196
 }
 
-// One thread per grid cell.  The cell takes template pixel (ty, tx) (nearest
-// resize); if that pixel is "occupied" the 3x3 opening decides whether it is a speck:
+// One thread per grid cell, OCC_FRAMES frames per block (the block's slice of the table is
+// staged in shared memory once and reused for every frame).  The cell takes template pixel
+// (ty, tx) (nearest resize); if that pixel is "occupied" the 3x3 opening decides whether it
+// is a speck:
 //   opened(p) = OR_{q in N3(p)} AND_{r in N3(q)} occ(r)   (erode ignores pixels outside
 //   the template, dilate treats them as 0 -- OpenCV default border values)
+static constexpr int OCC_FRAMES = 8;
+
 __global__ void __launch_bounds__(128)
-k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int8_t* __restrict__ grids) {
-  int cx = blockIdx.x * blockDim.x + threadIdx.x;
-  int cy = blockIdx.y;
-  int n = blockIdx.z;
-  if (cx >= g.Wc) return;
-  const uint8_t* lab = labels + (size_t)n * g.in_rows * g.in_cols;
-  // cv::resize INTER_NEAREST (bev.py:209-212): min(floor(d * ifx), src - 1) in fp64
-  int tx = min((int)floor(__dmul_rn((double)cx, g.ifx)), g.occ_w_px - 1);
-  int ty = min((int)floor(__dmul_rn((double)cy, g.ify)), g.occ_h_px - 1);
-  int v = template_px(lab, g, tx, ty);
-  if (is_occ(v, g.binary)) {
-    // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i); outside = "ignore"
-    unsigned occ = 0, inside = 0;
-    for (int j = 0; j < 5; ++j) {
-      int y = ty - 2 + j;
-      if (y < 0 || y >= g.occ_h_px) continue;
-      for (int i = 0; i < 5; ++i) {
-        int x = tx - 2 + i;
-        if (x < 0 || x >= g.occ_w_px) continue;
-        unsigned bit = 1u << (j * 5 + i);
-        inside |= bit;
-        int u = (i == 2 && j == 2) ? v : template_px(lab, g, x, y);
-        if (is_occ(u, g.binary)) occ |= bit;
+k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __restrict__ grids) {
+  const uint2* __restrict__ table = g.table;
+  __shared__ uint2 tab[25][128];
+  const int cells = g.Hc * g.Wc;
+  const int cell = blockIdx.x * 128 + threadIdx.x;
+  const bool live = cell < cells;
+  unsigned inside = 0;
+#pragma unroll
+  for (int pos = 0; pos < 25; ++pos) {
+    uint2 e = live ? table[(size_t)pos * cells + cell] : make_uint2(0u, 0u);
+    tab[pos][threadIdx.x] = e;
+    if (e.y & (1u << 16)) inside |= 1u << pos;
+  }
+  if (!live) return;               // each thread reads back only its own column: no barrier needed
+  const int cx = cell % g.Wc, cy = cell / g.Wc;
+  const size_t o = g.ros_layout ? (size_t)(g.Wc - 1 - cx) * g.Hc + (g.Hc - 1 - cy)   // occgrid_to_ros.py:18-21
+                                : (size_t)cell;
+  const int rows = g.in_rows, cols = g.in_cols;
+  const int n1 = min(B, (int)(blockIdx.y + 1) * OCC_FRAMES);
+  for (int n = blockIdx.y * OCC_FRAMES; n < n1; ++n) {
+    const uint8_t* lab = labels + (size_t)n * rows * cols;
+    int v = occ_sample(lab, tab[12][threadIdx.x], rows, cols);
+    if (is_occ(v, g.binary)) {
+      // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i)
+      unsigned occ = 1u << 12;
+      for (int pos = 0; pos < 25; ++pos) {
+        if (pos == 12 || !(inside & (1u << pos))) continue;
+        if (is_occ(occ_sample(lab, tab[pos][threadIdx.x], rows, cols), g.binary)) occ |= 1u << pos;
       }
+      bool opened = false;
+#pragma unroll
+      for (int qj = 1; qj <= 3; ++qj)
+#pragma unroll
+        for (int qi = 1; qi <= 3; ++qi) {
+          unsigned qbit = 1u << (qj * 5 + qi);
+          if (!(inside & qbit)) continue;            // dilate: outside contributes 0
+          unsigned nb = 0;
+#pragma unroll
+          for (int rj = -1; rj <= 1; ++rj)
+#pragma unroll
+            for (int ri = -1; ri <= 1; ++ri) nb |= 1u << ((qj + rj) * 5 + (qi + ri));
+          // erode: every in-template neighbour must be occupied
+          if (((~occ) & inside & nb) == 0) opened = true;
+        }
+      if (!opened) v = 2;                             // bev.py:203-205
     }
-    bool opened = false;
-#pragma unroll
-    for (int qj = 1; qj <= 3; ++qj)
-#pragma unroll
-      for (int qi = 1; qi <= 3; ++qi) {
-        unsigned qbit = 1u << (qj * 5 + qi);
-        if (!(inside & qbit)) continue;            // dilate: outside contributes 0
-        unsigned nb = 0;
-#pragma unroll
-        for (int rj = -1; rj <= 1; ++rj)
-#pragma unroll
-          for (int ri = -1; ri <= 1; ++ri) nb |= 1u << ((qj + rj) * 5 + (qi + ri));
-        // erode: every in-template neighbour must be occupied
-        if (((~occ) & inside & nb) == 0) opened = true;
-      }
-    if (!opened) v = 2;                             // bev.py:203-205
+    int out;
+    if (g.binary) {
+      int m = (v * 100) & 255;                        // uint8 * 100 (bev.py:139-142)
+      out = (m == 0) ? 255 : ((200 - m) & 255);       // bev.py:143-144
+    } else {
+      if (v == 3) v = 1;                              // bev.py:242
+      out = (v == 0) ? 255 : ((200 - ((v * 100) & 255)) & 255);   // bev.py:244-245
+    }
+    grids[(size_t)n * cells + o] = (int8_t)out;
   }
-  int out;
-  if (g.binary) {
-    int m = (v * 100) & 255;                        // uint8 * 100 (bev.py:139-142)
-    out = (m == 0) ? 255 : ((200 - m) & 255);       // bev.py:143-144
-  } else {
-    if (v == 3) v = 1;                              // bev.py:242
-    out = (v == 0) ? 255 : ((200 - ((v * 100) & 255)) & 255);   // bev.py:244-245
-  }
-  size_t cells = (size_t)g.Hc * g.Wc;
-  size_t o = g.ros_layout ? (size_t)(g.Wc - 1 - cx) * g.Hc + (g.Hc - 1 - cy)   // occgrid_to_ros.py:18-21
-                          : (size_t)cy * g.Wc + cx;
-  grids[(size_t)n * cells + o] = (int8_t)out;
 }
 
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s) {
-  dim3 grid((g.Wc + 127) / 128, g.Hc, B);
-  k_occgrid<<<grid, 128, 0, s>>>(labels, g, grids);
+  dim3 grid((g.Hc * g.Wc + 127) / 128, (B + OCC_FRAMES - 1) / OCC_FRAMES);
+  k_occgrid<<<grid, 128, 0, s>>>(labels, g, B, grids);
 }
 
 }  // namespace bc
