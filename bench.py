@@ -32,6 +32,11 @@ GRID = (10.0, 10.0, 0.1)
 CAL = "A"
 METRIC = "enet_frame_to_occupancy_grid_frames_per_s"
 N_INPUT_SETS = 4          # 4 x 100 MB of frames rotate through the steps (> 126 MB L2)
+# Weights: the reference's trained blobs are absent, so the default is the ENet architecture
+# briefly trained on a synthetic colour-region task (trained-like statistics), fed frames of the
+# same kind ("scene"); --weights seed42 --frames noise gives random init on white noise.
+WEIGHT_FILES = {"trained": "enet_synthetic_trained.bcw", "seed42": "enet_synthetic_seed42.bcw"}
+WEIGHTS, FRAMES = "trained", "scene"
 
 
 def peaks():
@@ -43,38 +48,63 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML from a thread every
+    5 ms (nvidia-smi -lms as the fallback, its start-up alone outlasts a 100 ms region)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.reasons, self.max_sm = index, [], set(), None
+        self._stop = threading.Event()
+        self.t = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self.BAD.items():
+                if r & bit:
+                    self.reasons.add(name)
+            time.sleep(0.005)
+
+    def _smi_loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+            except (OSError, subprocess.SubprocessError):
+                return
+            c = [x.strip() for x in out.strip().split(",")]
+            if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                self.sm.append(float(c[0]))
+                self.max_sm = float(c[1])
+                self.reasons |= {names[i] for i in range(4) if c[2 + i] == "Active"}
+
+    def _run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def make_frames(rank, n_sets):
@@ -83,9 +113,21 @@ def make_frames(rank, n_sets):
     from bugcar_image_segmentation_b200 import synth
     sets = []
     for k in range(n_sets):
-        base = synth.frames(32, 1234 + k * 100000 + rank * BATCH)
+        s0 = 1234 + k * 100000 + rank * BATCH
+        if FRAMES == "scene":
+            base = np.stack([synth.region_frame(s0 + i)[0] for i in range(32)])
+        else:
+            base = synth.frames(32, s0)
         sets.append(np.ascontiguousarray(np.tile(base, (BATCH // 32, 1, 1, 1))))
     return sets
+
+
+def workload_config(B):
+    return {"workload": f"full pipeline frame->ENet->argmax/LUT->BEV grid, bs {B} per GPU, 256x512 BGR frames, "
+                        f"15 classes, calibration {CAL} (500x500 warp), grid 10x10 m @ 0.1 m",
+            "weights": WEIGHT_FILES[WEIGHTS] + (" (ENet architecture, briefly trained on synthetic colour-region scenes)"
+                                                if WEIGHTS == "trained" else " (random init, BN calibrated)"),
+            "frames": "synthetic colour-region scenes + noise" if FRAMES == "scene" else "uniform noise / blocky"}
 
 
 def cpu_reference_step(w, eps, frames, cal, torch_threads):
@@ -112,11 +154,11 @@ def run_reference(args):
     from bugcar_image_segmentation_b200 import synth, weights as W
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    with open(os.path.join(ROOT, "pretrained_models", "enet_synthetic_seed42.bcw"), "rb") as f:
+    with open(os.path.join(ROOT, "pretrained_models", WEIGHT_FILES[WEIGHTS]), "rb") as f:
         w, nc, eps = W.unpack_flat(f.read())
     cal = synth.calibration(CAL)
-    per_step = 4                                   # bounded sample of the 256-frame batch
-    frames = synth.frames(per_step, 1234)
+    per_step = 16                                  # bounded sample of the 256-frame batch
+    frames = make_frames(0, 1)[0][:per_step]
     for _ in range(args.warmup):
         cpu_reference_step(w, eps, frames[:1], cal, threads)
     t0 = time.perf_counter()
@@ -129,14 +171,17 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"full pipeline frame->grid, calibration {CAL}, grid 10x10 m @ 0.1 m; CPU restatement "
-                               "(torch fp32 ENet + OpenCV pre/post); TensorFlow/Keras not installable here"},
+        "config": dict(workload_config(BATCH),
+                       reference_arm="CPU restatement of the reference path (reference preprocess semantics, torch fp32 "
+                                     "ENet, NumPy argmax/LUT, OpenCV create_occupancy_grid); TensorFlow/Keras and the "
+                                     "reference's model blobs are not available here"),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def main():
+    global WEIGHTS, FRAMES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -147,7 +192,10 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
+    ap.add_argument("--weights", default=WEIGHTS, choices=sorted(WEIGHT_FILES))
+    ap.add_argument("--frames", default=FRAMES, choices=["scene", "noise"])
     args = ap.parse_args()
+    WEIGHTS, FRAMES = args.weights, args.frames
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -167,7 +215,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     B = args.batch
 
-    wpath = os.path.join(ROOT, "pretrained_models", "enet_synthetic_seed42.bcw")
+    wpath = os.path.join(ROOT, "pretrained_models", WEIGHT_FILES[WEIGHTS])
     model = ENET(wpath, device=local, max_batch=B, precision="bf16")
     if args.chunk:
         model.ctx.set_chunk(args.chunk)
@@ -237,14 +285,16 @@ def main():
     l0 = model.ctx.launch_count()
     ms = timed(step_device, args.steps)
     launches = model.ctx.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end through the host entry point
     for i in range(args.warmup):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    step_e2e(0)                                          # untimed: grids of input set 0 for the CPU cross-check
+    torch.cuda.synchronize()
     grids_check = pinned_out.numpy()[:B].copy()
 
     # ---- per-kernel profile (events around every launch), rank 0 at any N
@@ -263,8 +313,12 @@ def main():
             k["tflops"] = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
         kernels.sort(key=lambda k: -k["ms"])
         top = kernels[0]
+        traffic = None      # dram bytes per launch of that kernel from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(top["kernel"], {}).get("dram_bytes_per_launch")
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                    "frac": top["gbs"] / hbm, "traffic": None, "peak_source": which,
+                    "frac": top["gbs"] / hbm, "traffic": traffic, "peak_source": which,
                     "share_of_step": top["share"], "avg_launch_us": top["ms"] * 1e3 / top["launches"],
                     "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                     "whole_path": {"algorithmic_gbs": sum(k["bytes"] for k in kernels) / (tot * 1e-3) / 1e9,
@@ -294,14 +348,18 @@ def main():
         torch.set_num_threads(threads)
         with open(wpath, "rb") as f:
             w, nc, eps = W.unpack_flat(f.read())
-        sample = host_sets[0][:6]
-        cpu_reference_step(w, eps, sample[:1], cal, threads)
-        t0 = time.perf_counter()
-        ref_grids = cpu_reference_step(w, eps, sample, cal, threads)
+        cpu_reference_step(w, eps, host_sets[0][:1], cal, threads)
+        ref_grids, t0, budget_s = [], time.perf_counter(), 12.0
+        for i in range(B):                           # bounded sample: frames of the batch until ~12 s of CPU work
+            ref_grids += cpu_reference_step(w, eps, host_sets[0][i:i + 1], cal, threads)
+            if time.perf_counter() - t0 > budget_s:
+                break
         dt = time.perf_counter() - t0
-        same = float(np.mean([np.mean(ref_grids[i] == grids_check[i]) for i in range(len(sample))]))
-        cpu = {"value": len(sample) / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"{len(sample)} frames of the batch, per-frame calls (torch fp32 ENet + OpenCV pre/post)",
+        nref = len(ref_grids)
+        same = float(np.mean([np.mean(ref_grids[i] == grids_check[i]) for i in range(nref)]))
+        cpu = {"value": nref / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"first {nref} frames of the batch ({dt:.1f} s), per-frame calls as the reference's loop makes them "
+                         "(torch fp32 ENet + OpenCV pre/post)",
                "grid_cell_agreement_bf16_vs_cpu_fp32": same}
 
     if rank == 0:
@@ -309,12 +367,10 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"full pipeline frame->ENet->argmax/LUT->BEV grid, bs {B} per GPU, 256x512 BGR frames, "
-                                   f"15 classes, calibration {CAL} (500x500 warp), grid 10x10 m @ 0.1 m",
-                       "weights": "enet_synthetic_seed42.bcw (random init, BN calibrated)",
-                       "l2": f"{N_INPUT_SETS} input sets x {B * 393216 / 1e6:.0f} MB rotate (> 126 MB L2)",
-                       "parallelism": f"frame-sharded dp{world}" + (", grids gathered to rank 0 (NCCL)" if world > 1 else ""),
-                       "chunk": args.chunk, "tensor_cores": not args.no_tc},
+            "config": dict(workload_config(B),
+                       l2=f"{N_INPUT_SETS} input sets x {B * 393216 / 1e6:.0f} MB rotate (> 126 MB L2)",
+                       parallelism=f"frame-sharded dp{world}" + (", grids gathered to rank 0 (NCCL)" if world > 1 else ""),
+                       chunk=args.chunk, tensor_cores=not args.no_tc),
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
