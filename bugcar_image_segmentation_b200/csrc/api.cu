@@ -468,6 +468,23 @@ int upload_net(bc_ctx* c) {
           return fail(c, BC_ERR_CUDA, "building the tcgen05 upsampling operands failed");
         continue;
       }
+      if (b.kind == 0) {     // down-sampling bottleneck: 3x3 conv + expansion + pooled residual + next projection
+        const HostBlock& hb = c->h_blocks[i];
+        if (i + 1 >= c->blocks.size() || !umma_supported(c->blocks[i + 1]) || c->blocks[i + 1].cin != b.cout) continue;
+        const HostBlock& nx = c->h_blocks[i + 1];
+        const int cip = 16;                         // internal width zero-padded to the K granularity (4 -> 16 at stage 1)
+        std::vector<float> cw((size_t)9 * cip * cip, 0.f), cb(cip, 0.f), ca(cip, 1.f), ew((size_t)cip * b.cout, 0.f);
+        for (int t = 0; t < 9; ++t)
+          for (int k = 0; k < b.ci; ++k)
+            for (int o = 0; o < b.ci; ++o) cw[((size_t)t * cip + k) * cip + o] = hb.c2.w[((size_t)t * b.ci + k) * b.ci + o];
+        for (int o = 0; o < b.ci; ++o) { cb[o] = hb.c2.bias[o]; ca[o] = hb.c2.alpha[o]; }
+        for (int k = 0; k < b.ci; ++k)
+          for (int o = 0; o < b.cout; ++o) ew[(size_t)k * b.cout + o] = hb.c3.w[(size_t)k * b.cout + o];
+        if (!umma_build(b.um_a, b.cout, cip, nx.ci, b.cin, cw.data(), 9, cb.data(), ca.data(), ew.data(), hb.c3.bias.data(),
+                        hb.c3.alpha.data(), hb.alpha_out.data(), nx.c1.w.data(), nx.c1.bias.data(), nx.c1.alpha.data()))
+          return fail(c, BC_ERR_CUDA, "building the tcgen05 down-sampling operands failed");
+        continue;
+      }
       if (!umma_supported(b)) continue;
       const HostBlock& hb = c->h_blocks[i];
       const HostBlock* nx = nullptr;
@@ -478,12 +495,12 @@ int upload_net(bc_ctx* c) {
       const float* na = nx ? nx->c1.alpha.data() : nullptr;
       bool ok;
       if (b.kind == 1) {
-        ok = umma_build(b.um_a, b.cin, b.ci, hb.c2.w.data(), 9, hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
+        ok = umma_build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 9, hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
                         hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
       } else {
-        ok = umma_build(b.um_a, b.cin, b.ci, hb.c2.w.data(), 5, hb.c2.bias.data(), hb.c2.alpha.data(), nullptr, nullptr,
+        ok = umma_build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 5, hb.c2.bias.data(), hb.c2.alpha.data(), nullptr, nullptr,
                         nullptr, nullptr, nullptr, nullptr, nullptr) &&
-             umma_build(b.um_b, b.cin, b.ci, hb.c2b.w.data(), 5, hb.c2b.bias.data(), hb.c2b.alpha.data(), hb.c3.w.data(),
+             umma_build(b.um_b, b.cin, b.ci, b.ci, b.cin, hb.c2b.w.data(), 5, hb.c2b.bias.data(), hb.c2b.alpha.data(), hb.c3.w.data(),
                         hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
@@ -574,10 +591,27 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       H /= 2; W /= 2;
       uint8_t* idx = b.cin == 16 ? c->idx1 : c->idx2;
       double px = (double)n * H * W;
-      L(c, "down_pool_conv2x2", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + b.ci * esz), 2.0 * px * 4 * b.cin * b.ci, s,
-        [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, s); });
-      conv("down_conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, 1));
-      conv("down_expand_add", E2, Y, P, b.cin, b.c3, b.alpha_out, t1);
+      bool tc = false;
+      if constexpr (std::is_same<T, bf16>::value) tc = c->tensor_cores && c->umma_ready && b.um_a.wblob != nullptr;
+      const int cip = tc ? b.um_a.CI : b.ci;       // e1 width as stored (zero-padded to 16 for tcgen05)
+      L(c, "down_pool_conv2x2", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + cip * esz), 2.0 * px * 4 * b.cin * b.ci, s,
+        [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, tc && cip != b.ci, s); });
+      if (tc) {
+        if constexpr (std::is_same<T, bf16>::value) {
+          cudaError_t ce = cudaSuccess;
+          L(c, b.cout == 64 ? "umma_down64" : "umma_down128", px * (cip + b.cin + b.cout + b.um_a.CN) * esz,
+            2.0 * px * (9.0 * b.ci * b.ci + (double)b.ci * b.cout + (double)b.cout * b.um_a.CN), s,
+            [&] { ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)P, (bf16*)Y, (bf16*)E2, n, H, W, taps_for(3, 3, 1), 0, 1,
+                                   c->num_sms, s); });
+          if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 down-sampling launch: ") + cudaGetErrorString(ce));
+          std::swap(E1, E2);          // e1' of the next block was written to E2
+          e1_ready = true;
+        }
+      } else {
+        e1_ready = false;
+        conv("down_conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, 1));
+        conv("down_expand_add", E2, Y, P, b.cin, b.c3, b.alpha_out, t1);
+      }
       std::swap(X, Y);
     } else if (b.kind == 1 || b.kind == 2) {
       bool done = false;

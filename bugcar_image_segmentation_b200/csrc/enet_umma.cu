@@ -16,6 +16,11 @@
 // Operands are K-major in shared memory in the canonical swizzled layouts (32/64/128-byte
 // rows), the same layouts TMA writes.
 //
+// Down-sampling bottlenecks reuse the kernel ("narrow residual", CRES < C): e1 is then the output
+// of the strided 2x2 conv (simt_down.cu), the residual is the max-pooled input with CRES channels
+// (the remaining C - CRES output channels get no residual: the zero padding of the main branch),
+// y has its own buffer per group, and the next block's projection may be wider than CI (CN).
+//
 // Reference: the regular / dilated / asymmetric bottlenecks of the frozen ENet graph the
 // reference executes (models.py:43-44); semantics in oracle/enet_oracle.py `regular`.
 #include "umma_common.cuh"
@@ -41,36 +46,42 @@ struct UmmaParams {
 };
 
 // weight image (identical in global and shared memory): offsets relative to its start
-template <int C, int CI>
+template <int C, int CI, int CN>
 struct UmmaWeights {
   static constexpr int RB = CI * 2;                 // row bytes of the CI-wide operands (64 / 32)
   static constexpr int W2_TAP = CI * RB;            // one tap of W2: [CI out][CI in]
   static constexpr int W3_BYTES = C * RB;           // [C out][CI in]
   static constexpr int NSUB = C / 64;
-  static constexpr int W1_SUB = CI * 128;           // [CI out][64 in] sub-tile of the next projection
+  static constexpr int W1_SUB = CN * 128;           // [CN out][64 in] sub-tile of the next projection
   static constexpr int OFF_W2 = 0;
   static constexpr int OFF_W3 = 9 * W2_TAP;
   static constexpr int OFF_W1 = ((9 * W2_TAP + W3_BYTES + 1023) / 1024) * 1024;   // 128-byte swizzle: 1 KB aligned
   static constexpr int W_BYTES = OFF_W1 + NSUB * W1_SUB;
-  static constexpr int NF = 4 * CI + 3 * C;         // fp32 parameter block
+  static constexpr int NF = 2 * CI + 3 * C + 2 * CN;   // fp32 parameter block
 };
 
-// NG = epilogue groups per CTA (tiles in flight), MINB = CTAs per SM
-template <int C, int CI, int NG_, int MINB_>
+// CN = width of the next block's projection, CRES = residual channels (C: regular bottleneck,
+// < C: down-sampling bottleneck), NG = epilogue groups per CTA (tiles in flight), MINB = CTAs per SM
+template <int C, int CI, int CN, int CRES, int NG_, int MINB_>
 struct UmmaSmem {
-  using Wt = UmmaWeights<C, CI>;
+  using Wt = UmmaWeights<C, CI, CN>;
   static constexpr int NG = NG_, MINB = MINB_;
+  static constexpr bool NARROW = CRES < C;
   static constexpr int THREADS = 128 + 128 * NG;
   static constexpr int RB = CI * 2;
   static constexpr int TAP_BYTES = 128 * RB;        // one A tap tile
   static constexpr int XSUB = 128 * 128;            // one 64-channel sub-tile of x / y
   static constexpr int NSUB = C / 64;
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
-  static constexpr int NX = NG + 1;                 // x / y tile ring (one tile of prefetch)
+  static constexpr int NX = NG + 1;                 // residual tile ring (one tile of prefetch)
+  static constexpr int NY = NARROW ? NG : NX;       // C-wide tiles: x/y in place, or one y per group
+  static constexpr int RES_RB = CRES * 2 >= 128 ? 128 : CRES * 2;   // row bytes / swizzle of a narrow residual tile
+  static constexpr int RBUF = NARROW ? 128 * CRES * 2 : 0;
   static constexpr int NRING = (MINB == 1 && CI == 16) ? 18 : 9;   // conv-tap ring slots
   // offsets (all multiples of 1024)
   static constexpr int OFF_X = 0;
-  static constexpr int OFF_TAPS = OFF_X + NX * XBUF;
+  static constexpr int OFF_R = OFF_X + NY * XBUF;
+  static constexpr int OFF_TAPS = OFF_R + NX * RBUF;
   static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;         // one e2 tile per group
   static constexpr int OFF_W = OFF_E2 + NG * TAP_BYTES;               // weight image starts here
   static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
@@ -87,7 +98,7 @@ struct UmmaSmem {
   static_assert(TOTAL + 1024 <= 232448 && (TOTAL + 2048) * MINB <= 233472, "shared memory budget");
   // TMEM columns: every group owns a D1 / D2 / D3 accumulator
   static constexpr uint32_t COL_D1 = 0, COL_D2 = NG * CI, COL_D3 = NG * (CI + C);
-  static constexpr uint32_t COLS_USED = NG * (2 * CI + C);
+  static constexpr uint32_t COLS_USED = NG * (CI + C + CN);
   static constexpr uint32_t TMEM_COLS = COLS_USED <= 32 ? 32 : COLS_USED <= 64 ? 64 : COLS_USED <= 128 ? 128
                                         : COLS_USED <= 256 ? 256 : 512;
   static_assert(COLS_USED <= 512 && TMEM_COLS * MINB <= 512, "TMEM budget");
@@ -106,22 +117,24 @@ struct UmmaSmem {
 //   warps 4.. epilogue       group g = (warp - 4) / 4; one TMEM lane (= pixel) per thread:
 //                            D1 -> e2 (smem), D2 + x -> y (smem, TMA store), D3 -> e1' (global);
 //                            its first thread stores y and requests the x tile that reuses the buffer
-template <int C, int CI, int NG, int MINB>
+template <int C, int CI, int CN, int CRES, int NG, int MINB>
 __global__ void __launch_bounds__(128 + 128 * NG, MINB)
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
+                                                                // (narrow: [pixels][CRES], box [128 px][CRES])
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
                   const UmmaParams p) {
-  using S = UmmaSmem<C, CI, NG, MINB>;
-  using Wt = UmmaWeights<C, CI>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB>;
+  using Wt = UmmaWeights<C, CI, CN>;
   constexpr int RB = S::RB;
   constexpr int NX = S::NX;
+  constexpr bool NARROW = S::NARROW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic shared memory is only guaranteed 16-byte aligned: align by hand (1 KB slack requested)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   float* sf = (float*)(smem + S::OFF_F);
-  const float *b2 = sf, *a2 = sf + CI, *b3 = sf + 2 * CI, *a3 = b3 + C, *aout = a3 + C, *b1n = aout + C, *a1n = b1n + CI;
+  const float *b2 = sf, *a2 = sf + CI, *b3 = sf + 2 * CI, *a3 = b3 + C, *aout = a3 + C, *b1n = aout + C, *a1n = b1n + CN;
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[S::NBARS];
@@ -148,7 +161,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr uint32_t IDESC_CONV = instr_desc(128, CI), IDESC_EXP = instr_desc(128, C), IDESC_PROJ = instr_desc(128, CI);
+  constexpr uint32_t IDESC_CONV = instr_desc(128, CI), IDESC_EXP = instr_desc(128, C), IDESC_PROJ = instr_desc(128, CN);
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // my tiles
   const bool full = !p.conv_only;
 
@@ -158,9 +171,14 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       if (full)                                          // first NX residual tiles; the rest are
         for (int k = 0; k < T && k < NX; ++k) {          // requested by the thread that frees a buffer
           const int tile = blockIdx.x + k * gridDim.x;
-          mbar_expect_tx(bar(S::X_FULL + k), S::XBUF);
-          for (int s = 0; s < S::NSUB; ++s)
-            tma_load_2d(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k));
+          if constexpr (NARROW) {
+            mbar_expect_tx(bar(S::X_FULL + k), S::RBUF);
+            tma_load_2d(sbase + S::OFF_R + k * S::RBUF, &map_x, 0, tile * 128, bar(S::X_FULL + k));
+          } else {
+            mbar_expect_tx(bar(S::X_FULL + k), S::XBUF);
+            for (int s = 0; s < S::NSUB; ++s)
+              tma_load_2d(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k));
+          }
         }
       int slot = 0, round = 0;
       for (int k = 0; k < T; ++k) {
@@ -217,12 +235,12 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       mbar_wait(bar(S::W_FULL), 0);
       for (int k = 0; k < T; ++k) {
         const int g = k % NG;
-        const uint32_t xs = sbase + S::OFF_X + (k % NX) * S::XBUF;
+        const uint32_t xs = sbase + S::OFF_X + (NARROW ? g : k % NX) * S::XBUF;
         mbar_wait(bar(S::Y_FULL + g), (k / NG) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < C / 16; ++kk)
-          umma_bf16(tmem + S::COL_D3 + g * CI, smem_desc<128>(xs + (kk / 4) * S::XSUB + (kk % 4) * 32),
+          umma_bf16(tmem + S::COL_D3 + g * CN, smem_desc<128>(xs + (kk / 4) * S::XSUB + (kk % 4) * 32),
                     smem_desc<128>(sbase + S::OFF_W1 + (kk / 4) * Wt::W1_SUB + (kk % 4) * 32), IDESC_PROJ, kk != 0);
         umma_commit(bar(S::D3_FULL + g));
       }
@@ -265,9 +283,10 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         fence_proxy_async();
         mbar_arrive(bar(S::E2_FULL + grp));
       }
-      // ---- epilogue 2: +bias, PReLU, + residual, PReLU, bf16 -> y tile (in place over x)
+      // ---- epilogue 2: +bias, PReLU, + residual, PReLU, bf16 -> y tile (in place over x; narrow: own buffer)
       const int xb = k % NX;
-      uint8_t* xt = smem + S::OFF_X + xb * S::XBUF;
+      uint8_t* yt = smem + S::OFF_X + (NARROW ? grp : xb) * S::XBUF;
+      const uint8_t* rt = smem + S::OFF_R + xb * S::RBUF;         // narrow residual tile
       mbar_wait(bar(S::X_FULL + xb), (uint32_t)(k / NX) & 1);
       mbar_wait(bar(S::D2_FULL + grp), par);
       tc_fence_after();
@@ -275,12 +294,14 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
         tmem_ld32(tm_lane + S::COL_D2 + grp * C + c0, v);
-        uint8_t* xrow = xt + (c0 / 64) * S::XSUB;
+        uint8_t* yrow = yt + (c0 / 64) * S::XSUB;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 channels
           const int ch = c0 + 8 * c;
-          uint4* px = reinterpret_cast<uint4*>(xrow + swz<128>(m * 128 + ((ch % 64) / 8) * 16));
-          uint4 xr = *px;
+          uint4* py = reinterpret_cast<uint4*>(yrow + swz<128>(m * 128 + ((ch % 64) / 8) * 16));
+          uint4 xr = make_uint4(0u, 0u, 0u, 0u);      // channels beyond CRES: zero padding of the main branch
+          if constexpr (!NARROW) xr = *py;
+          else if (ch < CRES) xr = *reinterpret_cast<const uint4*>(rt + swz<S::RES_RB>(m * S::RES_RB + (ch / 8) * 16));
           const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
           float o[8];
 #pragma unroll
@@ -290,7 +311,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
             o[2 * qq] = prelu_f(prelu_f(v[j] + b3[c0 + j], a3[c0 + j]) + xf.x, aout[c0 + j]);
             o[2 * qq + 1] = prelu_f(prelu_f(v[j + 1] + b3[c0 + j + 1], a3[c0 + j + 1]) + xf.y, aout[c0 + j + 1]);
           }
-          *px = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          *py = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
         }
       }
       fence_proxy_async();
@@ -300,36 +321,47 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       if (storer) {
         mbar_wait(bar(S::Y_FULL + grp), par);
         for (int s = 0; s < S::NSUB; ++s)
-          tma_store_2d(&map_y, sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, s * 64, tile * 128);
+          tma_store_2d(&map_y, smem_u32(yt) + s * S::XSUB, s * 64, tile * 128);
         tma_store_commit();
+        if constexpr (NARROW) {                       // every thread has read the residual tile: refill it
+          if (k + NX < T) {
+            const int nt = blockIdx.x + (k + NX) * gridDim.x;
+            mbar_expect_tx(bar(S::X_FULL + xb), S::RBUF);
+            tma_load_2d(sbase + S::OFF_R + xb * S::RBUF, &map_x, 0, nt * 128, bar(S::X_FULL + xb));
+          }
+        }
       }
       // ---- epilogue 3: the next block's projection: +bias, PReLU, bf16 -> e1' (global)
       if (p.has_next) {
         mbar_wait(bar(S::D3_FULL + grp), par);
         tc_fence_after();
-        float v[CI];
-        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D3 + grp * CI, v); else tmem_ld16(tm_lane + S::COL_D3 + grp * CI, v);
+        float v[CN];
+        if constexpr (CN == 32) tmem_ld32(tm_lane + S::COL_D3 + grp * CN, v); else tmem_ld16(tm_lane + S::COL_D3 + grp * CN, v);
         tc_fence_before();
 #pragma unroll
-        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
-        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
+        for (int j = 0; j < CN; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
+        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CN);
 #pragma unroll
-        for (int c = 0; c < CI / 8; ++c)
+        for (int c = 0; c < CN / 8; ++c)
           o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
                             pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
       }
-      // the x/y buffer may be reloaded once the store has read it (and the projection MMAs,
-      // which the D3_FULL wait above covers, have consumed it)
-      // ... and this thread, which knows it first, requests the tile that uses the buffer next
+      // The y buffer may be overwritten once the store has read it (and the projection MMAs, which
+      // the D3_FULL wait above covers, have consumed it).  In place: the thread that knows first
+      // requests the x tile that reuses the buffer.  Narrow: the group owns the buffer, so its
+      // threads meet on a named barrier before the next tile's epilogue 2 writes it.
       if (storer) {
         tma_store_wait_read();
-        if (k + NX < T) {
-          const int nt = blockIdx.x + (k + NX) * gridDim.x;
-          mbar_expect_tx(bar(S::X_FULL + xb), S::XBUF);
-          for (int s = 0; s < S::NSUB; ++s)
-            tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb));
+        if constexpr (!NARROW) {
+          if (k + NX < T) {
+            const int nt = blockIdx.x + (k + NX) * gridDim.x;
+            mbar_expect_tx(bar(S::X_FULL + xb), S::XBUF);
+            for (int s = 0; s < S::NSUB; ++s)
+              tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb));
+          }
         }
       }
+      if constexpr (NARROW) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
     }
     if (storer) tma_store_wait_all();
   }
@@ -423,12 +455,12 @@ static void pack_rows(uint8_t* dst, int rows, int row_bytes, const std::vector<f
 }
 
 // Builds the device weight image + fp32 parameter block of one bottleneck.
-//   conv: folded [ntaps][CI][CI] (+bias/alpha); expand: [1][CI][C]; next: [1][C][CI] of the NEXT block (may be null)
-template <int C, int CI>
+//   conv: folded [ntaps][CI][CI] (+bias/alpha); expand: [1][CI][C]; next: [1][C][CN] of the NEXT block (may be null)
+template <int C, int CI, int CN>
 static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* conv_b, const float* conv_a,
                     const float* exp_w, const float* exp_b, const float* exp_a, const float* alpha_out,
                     const float* next_w, const float* next_b, const float* next_a) {
-  using S = UmmaWeights<C, CI>;
+  using S = UmmaWeights<C, CI, CN>;
   std::vector<uint8_t> img(S::W_BYTES, 0);
   std::vector<float> cw(conv_w, conv_w + (size_t)ntaps * CI * CI);
   for (int t = 0; t < ntaps; ++t) pack_rows(img.data() + S::OFF_W2 + t * S::W2_TAP, CI, S::RB, cw, CI, CI, t, 0);
@@ -437,32 +469,38 @@ static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* 
     pack_rows(img.data() + S::OFF_W3, C, S::RB, ew, CI, C, 0, 0);
   }
   if (next_w) {
-    std::vector<float> nw(next_w, next_w + (size_t)C * CI);
+    std::vector<float> nw(next_w, next_w + (size_t)C * CN);
     for (int s = 0; s < S::NSUB; ++s)
-      pack_rows(img.data() + S::OFF_W1 + s * S::W1_SUB, CI, 128, nw, C, CI, 0, s * 64);
+      pack_rows(img.data() + S::OFF_W1 + s * S::W1_SUB, CN, 128, nw, C, CN, 0, s * 64);
   }
   std::vector<float> f(S::NF, 0.f);
   float* b2 = f.data(); float* a2 = b2 + CI; float* b3 = a2 + CI; float* a3 = b3 + C; float* ao = a3 + C;
-  float* b1n = ao + C; float* a1n = b1n + CI;
+  float* b1n = ao + C; float* a1n = b1n + CN;
   for (int j = 0; j < CI; ++j) { b2[j] = conv_b[j]; a2[j] = conv_a[j]; }
   if (exp_w) for (int j = 0; j < C; ++j) { b3[j] = exp_b[j]; a3[j] = exp_a[j]; ao[j] = alpha_out[j]; }
-  if (next_w) for (int j = 0; j < CI; ++j) { b1n[j] = next_b[j]; a1n[j] = next_a[j]; }
+  if (next_w) for (int j = 0; j < CN; ++j) { b1n[j] = next_b[j]; a1n[j] = next_a[j]; }
   if (cudaMalloc(&out.wblob, S::W_BYTES) != cudaSuccess) return false;
   if (cudaMalloc(&out.fparams, f.size() * sizeof(float)) != cudaSuccess) return false;
   cudaMemcpy(out.wblob, img.data(), S::W_BYTES, cudaMemcpyHostToDevice);
   cudaMemcpy(out.fparams, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice);
-  out.C = C; out.CI = CI; out.ntaps = ntaps; out.has_exp = exp_w != nullptr; out.has_next = next_w != nullptr;
+  out.C = C; out.CI = CI; out.CN = CN; out.ntaps = ntaps; out.has_exp = exp_w != nullptr; out.has_next = next_w != nullptr;
   return true;
 }
 
-bool umma_build(UmmaPack& out, int C, int CI, const float* conv_w, int ntaps, const float* conv_b, const float* conv_a,
-                const float* exp_w, const float* exp_b, const float* exp_a, const float* alpha_out,
+// (C, CI, CN, CRES) combinations of the ENet graph: regular stage-2/3 and stage-1/4 bottlenecks,
+// downsample1_0 (internal width 4 zero-padded to 16) and downsample2_0
+bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* conv_w, int ntaps, const float* conv_b,
+                const float* conv_a, const float* exp_w, const float* exp_b, const float* exp_a, const float* alpha_out,
                 const float* next_w, const float* next_b, const float* next_a) {
-  if (C == 128 && CI == 32)
-    return build_t<128, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
-  if (C == 64 && CI == 16)
-    return build_t<64, 16>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
-  return false;
+  bool ok = false;
+  if (C == 128 && CI == 32 && CN == 32 && CRES == 128)
+    ok = build_t<128, 32, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
+  else if (C == 64 && CI == 16 && CN == 16 && (CRES == 64 || CRES == 16))
+    ok = build_t<64, 16, 16>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
+  else if (C == 128 && CI == 16 && CN == 32 && CRES == 64)
+    ok = build_t<128, 16, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
+  out.CRES = CRES;
+  return ok;
 }
 
 void umma_free(UmmaPack& p) {
@@ -471,16 +509,21 @@ void umma_free(UmmaPack& p) {
   p = UmmaPack();
 }
 
-template <int C, int CI, int NG, int MINB>
+template <int C, int CI, int CN, int CRES, int NG, int MINB>
 static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
-  using S = UmmaSmem<C, CI, NG, MINB>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB>;
   CUtensorMap me1, mx, my;
   if (!make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
-  // conv_only never touches x / y: reuse the e1 tensor as a valid placeholder address
-  if (!make_map_x(&mx, conv_only ? e1 : x, conv_only ? px * CI / C : px, C)) return cudaErrorInvalidValue;
-  if (!make_map_x(&my, conv_only ? e1 : y, conv_only ? px * CI / C : px, C)) return cudaErrorInvalidValue;
+  if (S::NARROW) {
+    if (!make_map_rows(&mx, x, px, CRES, 128, S::RES_RB)) return cudaErrorInvalidValue;
+    if (!make_map_x(&my, y, px, C)) return cudaErrorInvalidValue;
+  } else {
+    // conv_only never touches x / y: reuse the e1 tensor as a valid placeholder address
+    if (!make_map_x(&mx, conv_only ? e1 : x, conv_only ? px * CI / C : px, C)) return cudaErrorInvalidValue;
+    if (!make_map_x(&my, conv_only ? e1 : y, conv_only ? px * CI / C : px, C)) return cudaErrorInvalidValue;
+  }
   UmmaParams p{};
   p.num_tiles = (int)(px / 128);
   p.tiles_per_frame = H * W / 128;
@@ -495,18 +538,19 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   static bool attr_done = false;
   const int smem = S::TOTAL + 1024;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI, NG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI, CN, CRES, NG, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const int ctas = num_sms * MINB;
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  k_umma_bottleneck<C, CI, NG, MINB><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
+  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }
 
-// Tiles in flight per SM = epilogue groups per CTA x CTAs per SM.  Tuning knobs (measured on
-// B200): BC_UMMA_CFG64 / BC_UMMA_CFG128 = "<groups><ctas>", e.g. "22".
+// Tiles in flight per SM = epilogue groups per CTA x CTAs per SM.  Tuning knob (measured on
+// B200): BC_UMMA_CFG64 = "<groups><ctas>" for the 64-channel regular bottleneck.
 static int cfg_from_env(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && v[0] >= '1' && v[0] <= '4' && v[1] >= '1' && v[1] <= '2' && !v[2]) ? (v[0] - '0') * 10 + (v[1] - '0') : dflt;
@@ -515,19 +559,17 @@ static int cfg_from_env(const char* name, int dflt) {
 cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H, int W,
                         const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
   if (128 % W != 0 && W % 128 != 0) return cudaErrorInvalidValue;
-  static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 22), cfg128 = cfg_from_env("BC_UMMA_CFG128", 21);
-#define BC_LAUNCH(C_, CI_, NG_, MB_) \
-  return launch_one<C_, CI_, NG_, MB_>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s)
-  if (pk.C == 128 && pk.CI == 32) {
-    if (cfg128 == 11) BC_LAUNCH(128, 32, 1, 1);
-    BC_LAUNCH(128, 32, 2, 1);
+  static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 22);
+#define BC_LAUNCH(C_, CI_, CN_, CR_, NG_, MB_) \
+  return launch_one<C_, CI_, CN_, CR_, NG_, MB_>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s)
+  if (pk.C == 128 && pk.CI == 32 && pk.CRES == 128) BC_LAUNCH(128, 32, 32, 128, 2, 1);
+  if (pk.C == 64 && pk.CI == 16 && pk.CRES == 64) {
+    if (cfg64 == 12) BC_LAUNCH(64, 16, 16, 64, 1, 2);
+    if (cfg64 == 41) BC_LAUNCH(64, 16, 16, 64, 4, 1);
+    BC_LAUNCH(64, 16, 16, 64, 2, 2);
   }
-  if (pk.C == 64 && pk.CI == 16) {
-    if (cfg64 == 12) BC_LAUNCH(64, 16, 1, 2);
-    if (cfg64 == 41) BC_LAUNCH(64, 16, 4, 1);
-    if (cfg64 == 31) BC_LAUNCH(64, 16, 3, 1);
-    BC_LAUNCH(64, 16, 2, 2);
-  }
+  if (pk.C == 64 && pk.CI == 16 && pk.CRES == 16) BC_LAUNCH(64, 16, 16, 16, 2, 2);     // downsample1_0
+  if (pk.C == 128 && pk.CI == 16 && pk.CRES == 64) BC_LAUNCH(128, 16, 32, 64, 2, 1);   // downsample2_0
 #undef BC_LAUNCH
   return cudaErrorInvalidValue;
 }

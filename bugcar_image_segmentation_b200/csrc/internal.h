@@ -28,7 +28,7 @@ struct ConvP {
 struct UmmaPack {
   uint8_t* wblob = nullptr;
   float* fparams = nullptr;
-  int C = 0, CI = 0, ntaps = 0;
+  int C = 0, CI = 0, CN = 0, CRES = 0, ntaps = 0;   // output / internal / next-projection / residual channels
   bool has_exp = false, has_next = false;
 };
 
@@ -66,9 +66,10 @@ struct Net;   // forward (api.cu)
 template <typename T>
 void launch_initial(const void* x, int kind, int B, T* out, const float* w, const float* g,
                     const float* b, const float* alpha, const float* lut, cudaStream_t s);
+// pad16: write e1 with 16 channels (ci real + zeros), the K granularity of tcgen05
 template <typename T>
 void launch_down_a(const T* x, int B, int H, int W, int cin, int ci, T* pooled, uint8_t* idx,
-                   T* e1, const ConvP& c1, cudaStream_t s);
+                   T* e1, const ConvP& c1, bool pad16, cudaStream_t s);
 template <typename T>
 void launch_conv(const T* in, T* out, const T* res, int res_ch, const ConvP& c,
                  const float* alpha_out, int B, int H, int W, const Taps& taps, cudaStream_t s);
@@ -87,7 +88,7 @@ void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cud
 // next block's projection].  See enet_umma.cu for the data flow.
 bool umma_available();                        // driver exposes cuTensorMapEncodeTiled
 bool umma_supported(const Bottleneck& bn);    // regular / dilated / asymmetric at C = 64 or 128
-bool umma_build(UmmaPack& out, int C, int CI, const float* conv_w, int ntaps, const float* conv_b,
+bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* conv_w, int ntaps, const float* conv_b,
                 const float* conv_a, const float* exp_w, const float* exp_b, const float* exp_a,
                 const float* alpha_out, const float* next_w, const float* next_b, const float* next_a);
 void umma_free(UmmaPack& p);
