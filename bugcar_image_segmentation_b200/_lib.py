@@ -41,6 +41,8 @@ SIGNATURES = {
     "bc_occgrid": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp]),
     "bc_pipeline": (_i, [_vp, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _i, _vp, _vp, _vp]),
     "bc_pipeline_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _i, _vp, _vp]),
+    "bc_pipeline_host_submit": (_i, [_vp, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _i, _vp, _vp]),
+    "bc_pipeline_host_wait": (_i, [_vp, _i]),
     "bc_gather_setup": (_i, [_vp, _vp, _i, _i]),
     "bc_launch_count": (C.c_longlong, [_vp]),
     "bc_set_profile": (_i, [_vp, _i]),
@@ -191,6 +193,14 @@ class Context:
         self._ck(self.lib.bc_pipeline_host(self.h, _ptr(h_bgr), h, w, B, _lut(lut), float(w_m), float(h_m),
                                            float(cell_m), int(binary), int(ros_layout), _ptr(h_grids),
                                            _ptr(stream)))
+
+    def pipeline_host_submit(self, h_bgr, h, w, B, lut, w_m, h_m, cell_m, binary, ros_layout, h_grids, stream=None):
+        self._ck(self.lib.bc_pipeline_host_submit(self.h, _ptr(h_bgr), h, w, B, _lut(lut), float(w_m), float(h_m),
+                                                  float(cell_m), int(binary), int(ros_layout), _ptr(h_grids),
+                                                  _ptr(stream)))
+
+    def pipeline_host_wait(self, keep_in_flight=0):
+        self._ck(self.lib.bc_pipeline_host_wait(self.h, int(keep_in_flight)))
 
     def gather_setup(self, d_base, rank, world):
         self._ck(self.lib.bc_gather_setup(self.h, _ptr(d_base), int(rank), int(world)))

@@ -111,6 +111,14 @@ struct bc_ctx {
   size_t frames_in_bytes = 0;
   int8_t* d_grids_out = nullptr;
   size_t grids_out_bytes = 0;
+  // staging slots of bc_pipeline_host_submit (two steps in flight)
+  struct Slot {
+    uint8_t* d_in = nullptr; size_t in_bytes = 0;
+    int8_t* d_out = nullptr; size_t out_bytes = 0;
+    cudaEvent_t copied = nullptr, computed = nullptr, done = nullptr;
+    bool busy = false;
+  } slots[2];
+  long long submitted = 0;
 
   // ---- BEV
   bool bev_set = false;
@@ -642,6 +650,14 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           done = true;
         }
       }
+      if (!done && b.kind == 1 && b.cin == 16 && b.ci == 4 && b.dilation == 1) {
+        // stage 5: K = 4 is too skinny for tcgen05; one fused CUDA-core kernel, x in, y out
+        const double px = (double)n * H * W;
+        L(c, "stage5_bottleneck", px * 2.0 * b.cin * esz, 2.0 * px * (16.0 * 4 + 9.0 * 16 + 4.0 * 16), s,
+          [&] { launch_stage5<T>(X, Y, b, n, H, W, s); });
+        e1_ready = false;
+        done = true;
+      }
       if (!done) {
         e1_ready = false;
         conv("proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
@@ -989,6 +1005,11 @@ void bc_destroy(bc_ctx* c) {
   free_occ_tables(c);
   for (auto& r : c->prof) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  for (auto& sl : c->slots) {
+    if (sl.d_in) cudaFree(sl.d_in);
+    if (sl.d_out) cudaFree(sl.d_out);
+    for (cudaEvent_t e : {sl.copied, sl.computed, sl.done}) if (e) cudaEventDestroy(e);
+  }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto e : c->copy_done) if (e) cudaEventDestroy(e);
   if (c->call_start) cudaEventDestroy(c->call_start);
@@ -1271,6 +1292,77 @@ int bc_pipeline_host(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const
     f0 += nb;
   }
   CU(cudaStreamSynchronize(s));
+  return BC_OK;
+}
+
+// Streaming form of bc_pipeline_host: returns as soon as the work is enqueued.  Two staging
+// slots alternate, so the H2D copy of step i+1 (internal copy stream) overlaps the kernels of
+// step i (caller's stream) and the step time is max(copy, compute) instead of their sum.
+int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const uint8_t h_lut[256], double w_m,
+                            double h_m, double cell_m, int binary, int ros_layout, int8_t* h_grids, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!h_bgr || !h_grids || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
+  if (h < 1 || w < 1 || h > 16384 || w > 16384) return fail(c, BC_ERR_ARG, "bad frame shape");
+  if (B < 1 || B > c->max_batch) return fail(c, BC_ERR_ARG, "batch size outside [1, max_batch]");
+  if (!c->net_loaded) return fail(c, BC_ERR_STATE, "bc_load_enet has not been called");
+  BevGeom g;
+  int r = make_geom(c, w_m, h_m, cell_m, binary, ros_layout, g);
+  if (r) return r;
+  if (c->in_rows != BC_NET_H || c->in_cols != BC_NET_W)
+    return fail(c, BC_ERR_ARG, "calibration input size must be (256, 512) for the ENet pipeline (bev.py:169)");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  bc_ctx::Slot& sl = c->slots[c->submitted & 1];
+  const size_t in_bytes = (size_t)B * h * w * 3, out_bytes = (size_t)B * g.Hc * g.Wc;
+  if (sl.busy) { CU(cudaEventSynchronize(sl.done)); sl.busy = false; }      // at most two steps in flight
+  if (!sl.copied) {
+    CU(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
+  if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (sl.in_bytes < in_bytes || sl.out_bytes < out_bytes) {
+    CU(cudaDeviceSynchronize());
+    invalidate_graphs(c);
+    if (sl.in_bytes < in_bytes) {
+      if (sl.d_in) cudaFree(sl.d_in);
+      sl.d_in = nullptr; sl.in_bytes = 0;
+      CU(cudaMalloc(&sl.d_in, in_bytes));
+      sl.in_bytes = in_bytes;
+    }
+    if (sl.out_bytes < out_bytes) {
+      if (sl.d_out) cudaFree(sl.d_out);
+      sl.d_out = nullptr; sl.out_bytes = 0;
+      CU(cudaMalloc(&sl.d_out, out_bytes));
+      sl.out_bytes = out_bytes;
+    }
+  }
+  if ((r = ensure_scratch(c))) return r;
+  const ResizeTab* rt;
+  if ((r = get_resize_tab(c, h, w, &rt))) return r;   // may allocate: keep it out of capture
+  // the slot's previous kernels (two submits ago) were waited for above via `done`, which follows them
+  CU(cudaMemcpyAsync(sl.d_in, h_bgr, in_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  CU(cudaEventRecord(sl.copied, c->copy_stream));
+  CU(cudaStreamWaitEvent(s, sl.copied, 0));
+  if ((r = run_pipeline(c, sl.d_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, sl.d_out, s))) return r;
+  CU(cudaMemcpyAsync(h_grids, sl.d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(sl.done, s));
+  sl.busy = true;
+  c->submitted++;
+  return BC_OK;
+}
+
+// Blocks until at most `keep_in_flight` (0 or 1) submitted steps are still running; the grids
+// of every completed step are then in their host buffers.
+int bc_pipeline_host_wait(bc_ctx* c, int keep_in_flight) {
+  if (!c) return BC_ERR_ARG;
+  if (keep_in_flight < 0 || keep_in_flight > 1) return fail(c, BC_ERR_ARG, "keep_in_flight must be 0 or 1");
+  CU(cudaSetDevice(c->device));
+  // slots in submission order: the older one is the slot the NEXT submit would take
+  for (int k = 0; k < 2 - keep_in_flight; ++k) {
+    bc_ctx::Slot& sl = c->slots[(c->submitted + k) & 1];
+    if (sl.busy) { CU(cudaEventSynchronize(sl.done)); sl.busy = false; }
+  }
   return BC_OK;
 }
 

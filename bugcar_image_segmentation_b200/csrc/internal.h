@@ -80,6 +80,10 @@ template <typename T>
 void launch_fullconv(const T* x, int B, int C, const float* w, float* logits, uint8_t* labels,
                      const Lut256* lut, cudaStream_t s);
 
+// regular bottleneck at 16 channels / internal width 4 (regular5_1) fused into one kernel (simt_stage5.cu)
+template <typename T>
+void launch_stage5(const T* x, T* y, const Bottleneck& b, int B, int H, int W, cudaStream_t s);
+
 template <typename T>
 void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cudaStream_t s);
 

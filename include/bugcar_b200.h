@@ -148,6 +148,17 @@ int bc_pipeline_host(bc_ctx* ctx, const uint8_t* h_bgr, int h, int w, int B,
                      const uint8_t h_lut[256], double w_m, double h_m, double cell_m,
                      int binary, int ros_layout, int8_t* h_grids, void* stream);
 
+/* Streaming form for a driver loop that keeps the GPU busy: submit returns once the step is
+ * enqueued (H2D on an internal copy stream, kernels + D2H on `stream`); two staging slots
+ * alternate, so the copy of step i+1 overlaps the kernels of step i.  A third submit blocks until
+ * the oldest step has finished.  bc_pipeline_host_wait(ctx, k) returns when at most k (0 or 1)
+ * submitted steps are still in flight; the grids of finished steps are in their h_grids buffers,
+ * which (like h_bgr) must stay valid and should be pinned until then. */
+int bc_pipeline_host_submit(bc_ctx* ctx, const uint8_t* h_bgr, int h, int w, int B,
+                            const uint8_t h_lut[256], double w_m, double h_m, double cell_m,
+                            int binary, int ros_layout, int8_t* h_grids, void* stream);
+int bc_pipeline_host_wait(bc_ctx* ctx, int keep_in_flight);
+
 /* ---- multi-GPU gather (frame-batch sharding; grids gathered to rank 0) ----------------- */
 /* After this call bc_occgrid/bc_pipeline write their grids to
  * d_gather_base + rank * B * Hc * Wc instead of d_grids when d_grids == NULL.

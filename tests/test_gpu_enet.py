@@ -239,3 +239,30 @@ def test_full_batch_properties(setup):
     assert grids.shape == (256, 100, 100)
     assert np.array_equal(grids, small[idx])
     assert big.ctx.launch_count() > 0
+
+
+def test_streaming_host_entry_point(setup):
+    """bc_pipeline_host_submit / _wait (two staging slots, copy/compute overlap across steps)
+    returns the same grids as the blocking bc_pipeline_host, step after step."""
+    import torch
+    from bugcar_image_segmentation_b200 import _lib
+    from bugcar_image_segmentation_b200.bev import bev_transform_tools
+    from bugcar_image_segmentation_b200.pipeline import FramePipeline
+    m = setup["model"]
+    m.ctx.set_precision(_lib.BC_PREC_BF16)
+    c = synth.calibration("A")
+    bev = bev_transform_tools(c["input image size"], c["output image size"], c["distance to target"],
+                              c["tile_length"], c["cm_per_px"], c["yaw"], c["is_laserscan"])
+    bev._bev_matrix = np.asarray(c["bev matrix"]).reshape(3, 3)
+    pipe = FramePipeline(m, bev, 10.0, 10.0, 0.1)
+    frames = setup["frames"]
+    want = [pipe(frames[[i % 3, (i + 1) % 3]]) for i in range(5)]
+    ins = [torch.from_numpy(frames[[i % 3, (i + 1) % 3]].copy()).pin_memory() for i in range(5)]
+    outs = [torch.zeros((2, pipe.Hc, pipe.Wc), dtype=torch.int8).pin_memory() for _ in range(5)]
+    for i in range(5):
+        m.ctx.pipeline_host_submit(ins[i], 256, 512, 2, pipe.lut, 10.0, 10.0, 0.1, 0, 0, outs[i], None)
+        m.ctx.pipeline_host_wait(1)
+        if i >= 1:
+            assert np.array_equal(outs[i - 1].numpy(), want[i - 1]), i
+    m.ctx.pipeline_host_wait(0)
+    assert np.array_equal(outs[4].numpy(), want[4])
