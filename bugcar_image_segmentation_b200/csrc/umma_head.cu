@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(192, 1)
 k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][128][16], 32-byte swizzle
             const HeadParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + HEAD_OFF_BAR);
   enum { TAP_FULL0 = 0, TAP_FULL1, TAP_EMPTY0, TAP_EMPTY1, D_FULL0, D_FULL1, D_EMPTY0, D_EMPTY1, W_FULL, NBARS };

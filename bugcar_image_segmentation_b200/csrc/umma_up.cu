@@ -69,7 +69,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
   using S = UpSmem<CIN, CI, COUT>;
   constexpr int RB = S::RB, ORB = S::ORB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const uint32_t sbase = smem_u32(smem);
   float* sf = (float*)(smem + S::OFF_F);
   const float *bm = sf, *b1 = bm + COUT, *a1 = b1 + CI, *bt = a1 + CI, *at = bt + CI, *b3 = at + CI, *aout = b3 + COUT,
