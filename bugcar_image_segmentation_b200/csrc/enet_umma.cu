@@ -42,7 +42,10 @@ struct UmmaParams {
   int has_next;         // 1: compute the next block's projection from the y tile
   bf16* out_small;      // e2 (conv_only) or e1' (has_next): [pixels][CI]
   const uint8_t* wblob; // packed weights, exact shared-memory image (see UmmaSmem)
-  const float* fparams; // b2[CI] a2[CI] b3[C] a3[C] aout[C] b1n[CI] a1n[CI]
+  // fp32 bias / PReLU-slope block b2[CI] a2[CI] b3[C] a3[C] aout[C] b1n[CN] a1n[CN], by value: the
+  // epilogues index it with compile-time channel numbers, so every use is a constant-bank operand
+  // of the FADD / FMUL itself (no load instruction, no shared-memory traffic)
+  float f[512];
 };
 
 // weight image (identical in global and shared memory): offsets relative to its start
@@ -85,8 +88,7 @@ struct UmmaSmem {
   static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;         // one e2 tile per group
   static constexpr int OFF_W = OFF_E2 + NG * TAP_BYTES;               // weight image starts here
   static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
-  static constexpr int OFF_F = OFF_W + ((Wt::W_BYTES + 1023) / 1024) * 1024;
-  static constexpr int OFF_BAR = OFF_F + ((Wt::NF * 4 + 63) / 64) * 64;
+  static constexpr int OFF_BAR = OFF_W + ((Wt::W_BYTES + 1023) / 1024) * 1024;
   static constexpr int TOTAL = OFF_BAR + 1024;
   // barriers
   static constexpr int X_FULL = 0, D1_FULL = X_FULL + NX, D1_EMPTY = D1_FULL + NG,
@@ -123,7 +125,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                                                                 // (narrow: [pixels][CRES], box [128 px][CRES])
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
-                  const UmmaParams p) {
+                  const __grid_constant__ UmmaParams p) {
   using S = UmmaSmem<C, CI, CN, CRES, NG, MINB>;
   using Wt = UmmaWeights<C, CI, CN>;
   constexpr int RB = S::RB;
@@ -133,8 +135,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   // dynamic shared memory is only guaranteed 16-byte aligned: align by hand (1 KB slack requested)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const uint32_t sbase = smem_u32(smem);
-  float* sf = (float*)(smem + S::OFF_F);
-  const float *b2 = sf, *a2 = sf + CI, *b3 = sf + 2 * CI, *a3 = b3 + C, *aout = a3 + C, *b1n = aout + C, *a1n = b1n + CN;
+  constexpr int F_B2 = 0, F_A2 = CI, F_B3 = 2 * CI, F_A3 = F_B3 + C, F_AOUT = F_A3 + C, F_B1N = F_AOUT + C, F_A1N = F_B1N + CN;
+  static_assert(F_A1N + CN <= 512, "parameter block");
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[S::NBARS];
@@ -149,9 +151,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       mbar_init(bar(i), by_group ? 128 : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar(S::W_FULL), Wt::W_BYTES + Wt::NF * 4);
+    mbar_expect_tx(bar(S::W_FULL), Wt::W_BYTES);
     bulk_load(sbase + S::OFF_W, p.wblob, Wt::W_BYTES, bar(S::W_FULL));
-    bulk_load(sbase + S::OFF_F, p.fparams, Wt::NF * 4, bar(S::W_FULL));
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
@@ -266,7 +267,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tc_fence_before();
         mbar_arrive(bar(S::D1_EMPTY + grp));
 #pragma unroll
-        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b2[j], a2[j]);
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + p.f[F_B2 + j], p.f[F_A2 + j]);
         if (!full) {
           uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
 #pragma unroll
@@ -290,7 +291,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       mbar_wait(bar(S::X_FULL + xb), (uint32_t)(k / NX) & 1);
       mbar_wait(bar(S::D2_FULL + grp), par);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < C; c0 += 32) {
         float v[32];
         tmem_ld32(tm_lane + S::COL_D2 + grp * C + c0, v);
@@ -308,8 +309,9 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           for (int qq = 0; qq < 4; ++qq) {
             float2 xf = __bfloat1622float2(xh[qq]);
             int j = 8 * c + 2 * qq;
-            o[2 * qq] = prelu_f(prelu_f(v[j] + b3[c0 + j], a3[c0 + j]) + xf.x, aout[c0 + j]);
-            o[2 * qq + 1] = prelu_f(prelu_f(v[j + 1] + b3[c0 + j + 1], a3[c0 + j + 1]) + xf.y, aout[c0 + j + 1]);
+            o[2 * qq] = prelu_f(prelu_f(v[j] + p.f[F_B3 + c0 + j], p.f[F_A3 + c0 + j]) + xf.x, p.f[F_AOUT + c0 + j]);
+            o[2 * qq + 1] = prelu_f(prelu_f(v[j + 1] + p.f[F_B3 + c0 + j + 1], p.f[F_A3 + c0 + j + 1]) + xf.y,
+                                    p.f[F_AOUT + c0 + j + 1]);
           }
           *py = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
         }
@@ -339,7 +341,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         if constexpr (CN == 32) tmem_ld32(tm_lane + S::COL_D3 + grp * CN, v); else tmem_ld16(tm_lane + S::COL_D3 + grp * CN, v);
         tc_fence_before();
 #pragma unroll
-        for (int j = 0; j < CN; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
+        for (int j = 0; j < CN; ++j) v[j] = prelu_f(v[j] + p.f[F_B1N + j], p.f[F_A1N + j]);
         uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CN);
 #pragma unroll
         for (int c = 0; c < CN / 8; ++c)
@@ -480,9 +482,8 @@ static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* 
   if (exp_w) for (int j = 0; j < C; ++j) { b3[j] = exp_b[j]; a3[j] = exp_a[j]; ao[j] = alpha_out[j]; }
   if (next_w) for (int j = 0; j < CN; ++j) { b1n[j] = next_b[j]; a1n[j] = next_a[j]; }
   if (cudaMalloc(&out.wblob, S::W_BYTES) != cudaSuccess) return false;
-  if (cudaMalloc(&out.fparams, f.size() * sizeof(float)) != cudaSuccess) return false;
   cudaMemcpy(out.wblob, img.data(), S::W_BYTES, cudaMemcpyHostToDevice);
-  cudaMemcpy(out.fparams, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice);
+  out.hf = f;
   out.C = C; out.CI = CI; out.CN = CN; out.ntaps = ntaps; out.has_exp = exp_w != nullptr; out.has_next = next_w != nullptr;
   return true;
 }
@@ -534,7 +535,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   p.has_next = has_next;
   p.out_small = out_small;
   p.wblob = pk.wblob;
-  p.fparams = pk.fparams;
+  memcpy(p.f, pk.hf.data(), pk.hf.size() * sizeof(float));
   static bool attr_done = false;
   const int smem = S::TOTAL + 1024;
   if (!attr_done) {
