@@ -506,7 +506,6 @@ bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* con
 
 void umma_free(UmmaPack& p) {
   if (p.wblob) cudaFree(p.wblob);
-  if (p.fparams) cudaFree(p.fparams);
   p = UmmaPack();
 }
 

@@ -27,8 +27,7 @@ struct ConvP {
 // shared-memory image of the K-major swizzled bf16 weights + the fp32 bias / slope block
 struct UmmaPack {
   uint8_t* wblob = nullptr;
-  float* fparams = nullptr;    // device copy (umma_up.cu)
-  std::vector<float> hf;       // host copy, passed by value as kernel parameters (enet_umma.cu)
+  std::vector<float> hf;       // fp32 bias / slope block, passed by value as kernel parameters
   int C = 0, CI = 0, CN = 0, CRES = 0, ntaps = 0;   // output / internal / next-projection / residual channels
   bool has_exp = false, has_next = false;
 };

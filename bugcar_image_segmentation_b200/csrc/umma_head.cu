@@ -33,7 +33,8 @@ static constexpr int HEAD_OFF_LUT = HEAD_OFF_W + 4 * HEAD_WTAP;
 static constexpr int HEAD_OFF_BAR = HEAD_OFF_LUT + 256;
 static constexpr int HEAD_SMEM = HEAD_OFF_BAR + 128;
 
-__global__ void __launch_bounds__(192, 1)
+// 41 KB of shared memory and 128 TMEM columns per CTA: four CTAs per SM keep four tiles in flight
+__global__ void __launch_bounds__(192, 4)
 k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][128][16], 32-byte swizzle
             const HeadParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -179,7 +180,7 @@ cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, 
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  int grid = p.num_tiles < 4 * num_sms ? p.num_tiles : 4 * num_sms;
   k_umma_head<<<grid, 192, smem, s>>>(mx, p);
   return cudaGetLastError();
 }

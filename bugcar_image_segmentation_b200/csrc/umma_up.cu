@@ -24,7 +24,9 @@ struct UpParams {
   const uint8_t* idx;     // [low px][COUT] pool window position (2 bits)
   bf16* e1_next;          // [high px][16]
   const uint8_t* wblob;
-  const float* fparams;   // bm[COUT] b1[CI] a1[CI] bt[CI] at[CI] b3[COUT] aout[COUT] b1n[16] a1n[16]
+  // bm[COUT] b1[CI] a1[CI] bt[CI] at[CI] b3[COUT] aout[COUT] b1n[16] a1n[16], by value: constant-bank
+  // operands of the epilogue arithmetic (compile-time channel indices), no shared-memory traffic
+  float f[384];
 };
 
 template <int CIN, int CI, int COUT>
@@ -62,18 +64,18 @@ struct UpSmem {
 };
 
 template <int CIN, int CI, int COUT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, (COUT == 16 ? 2 : 1))
 k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box [128][64], 128-byte swizzle
           const __grid_constant__ CUtensorMap map_y,   // 2D [high px][COUT], box = one staged row
-          const UpParams p) {
+          const __grid_constant__ UpParams p) {
   using S = UpSmem<CIN, CI, COUT>;
   constexpr int RB = S::RB, ORB = S::ORB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const uint32_t sbase = smem_u32(smem);
-  float* sf = (float*)(smem + S::OFF_F);
-  const float *bm = sf, *b1 = bm + COUT, *a1 = b1 + CI, *bt = a1 + CI, *at = bt + CI, *b3 = at + CI, *aout = b3 + COUT,
-              *b1n = aout + COUT, *a1n = b1n + 16;
+  constexpr int F_BM = 0, F_B1 = COUT, F_A1 = F_B1 + CI, F_BT = F_A1 + CI, F_AT = F_BT + CI, F_B3 = F_AT + CI,
+                F_AOUT = F_B3 + COUT, F_B1N = F_AOUT + COUT, F_A1N = F_B1N + 16;
+  static_assert(F_A1N + 16 <= 384, "parameter block");
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
   enum { X_FULL0 = 0, X_FULL1, X_EMPTY0, X_EMPTY1, DA_FULL, E1_FULL, DB_FULL, E2_FULL, DC_FULL, OUT_FULL, OUT_EMPTY,
          DD_FULL, W_FULL, NBARS };
@@ -87,9 +89,8 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
     const int all[] = {E1_FULL, E2_FULL, OUT_FULL};
     for (int b : all) mbar_init(bar(b), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar(W_FULL), S::W_BYTES + S::NF * 4);
+    mbar_expect_tx(bar(W_FULL), S::W_BYTES);
     bulk_load(sbase + S::OFF_W, p.wblob, S::W_BYTES, bar(W_FULL));
-    bulk_load(sbase + S::OFF_F, p.fparams, S::NF * 4, bar(W_FULL));
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
@@ -179,7 +180,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
         float v[CI];
         if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_A + COUT, v); else tmem_ld16(tm_lane + S::COL_A + COUT, v);
 #pragma unroll
-        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + b1[j], a1[j]);
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + p.f[F_B1 + j], p.f[F_A1 + j]);
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
           *reinterpret_cast<uint4*>(smem + S::OFF_E1 + swz<RB>(m * RB + c * 16)) =
@@ -197,7 +198,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
         float v[CI];
         if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_B + t * CI, v); else tmem_ld16(tm_lane + S::COL_B + t * CI, v);
 #pragma unroll
-        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + bt[j], at[j]);
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + p.f[F_BT + j], p.f[F_AT + j]);
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
           *reinterpret_cast<uint4*>(smem + S::OFF_E2 + t * S::E_TILE + swz<RB>(m * RB + c * 16)) =
@@ -212,14 +213,14 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       if (k >= 1) mbar_wait(bar(OUT_EMPTY), (k - 1) & 1);
       tc_fence_after();
       const uint8_t* ip = p.idx + ((size_t)tile * 128 + m) * COUT;
-#pragma unroll 1
+#pragma unroll(COUT == 64 ? 1 : 4)   // 64 channels: a rolled loop (dynamic constant-bank index) beats 4x the code
       for (int c0 = 0; c0 < COUT; c0 += 16) {
         float mainv[16];
         tmem_ld16(tm_lane + S::COL_A + c0, mainv);
         const uint4 iv = *reinterpret_cast<const uint4*>(ip + c0);
         const uint8_t* ib = reinterpret_cast<const uint8_t*>(&iv);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) mainv[j] += bm[c0 + j];
+        for (int j = 0; j < 16; ++j) mainv[j] += p.f[F_BM + c0 + j];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           float v[16];
@@ -227,8 +228,8 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            float o0 = prelu_f(v[j] + b3[c0 + j] + (ib[j] == t ? mainv[j] : 0.f), aout[c0 + j]);
-            float o1 = prelu_f(v[j + 1] + b3[c0 + j + 1] + (ib[j + 1] == t ? mainv[j + 1] : 0.f), aout[c0 + j + 1]);
+            float o0 = prelu_f(v[j] + p.f[F_B3 + c0 + j] + (ib[j] == t ? mainv[j] : 0.f), p.f[F_AOUT + c0 + j]);
+            float o1 = prelu_f(v[j + 1] + p.f[F_B3 + c0 + j + 1] + (ib[j + 1] == t ? mainv[j + 1] : 0.f), p.f[F_AOUT + c0 + j + 1]);
             pk[j / 2] = pack_bf16(o0, o1);
           }
           // high-res pixel (2*lr + ky, 2*lx + kx) of this tile
@@ -264,7 +265,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
             float v[16];
             tmem_ld16(tm_lane + S::COL_D + r * 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j] + b1n[j], a1n[j]);
+            for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j] + p.f[F_B1N + j], p.f[F_A1N + j]);
             uint4* o = reinterpret_cast<uint4*>(p.e1_next + ((hrow0 + r) * Wh + m) * 16);
             o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
@@ -328,9 +329,8 @@ static bool up_build_t(UmmaPack& out, const float* wm, const float* bmv, const f
   memcpy(o, aoutv, COUT * 4); o += COUT;
   if (w1n) { memcpy(o, b1nv, 16 * 4); memcpy(o + 16, a1nv, 16 * 4); }
   if (cudaMalloc(&out.wblob, S::W_BYTES) != cudaSuccess) return false;
-  if (cudaMalloc(&out.fparams, f.size() * 4) != cudaSuccess) return false;
   cudaMemcpy(out.wblob, img.data(), S::W_BYTES, cudaMemcpyHostToDevice);
-  cudaMemcpy(out.fparams, f.data(), f.size() * 4, cudaMemcpyHostToDevice);
+  out.hf = f;
   out.C = CIN; out.CI = CI; out.ntaps = 4; out.has_exp = true; out.has_next = w1n != nullptr;
   return true;
 }
@@ -363,7 +363,7 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
   p.idx = idx;
   p.e1_next = e1_next;
   p.wblob = pk.wblob;
-  p.fparams = pk.fparams;
+  memcpy(p.f, pk.hf.data(), pk.hf.size() * sizeof(float));
   static bool attr_done = false;
   const int smem = S::TOTAL + 1024;
   if (!attr_done) {
@@ -371,7 +371,9 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  static_assert(COUT != 16 || ((S::TOTAL + 2048) * 2 <= 233472 && S::TMEM_COLS * 2 <= 512), "two CTAs per SM");
+  const int ctas = num_sms * (COUT == 16 ? 2 : 1);       // upsample5_0 fits twice per SM: two tiles in flight
+  int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   k_umma_up<CIN, CI, COUT><<<grid, 192, smem, s>>>(mx, my, p);
   return cudaGetLastError();
 }
