@@ -129,7 +129,7 @@ struct bc_ctx {
   // ---- resize tables, keyed by source size
   std::map<std::pair<int, int>, ResizeTab> resize_tabs;
   // ---- K9 coordinate tables, keyed by the geometry (cleared by bc_set_bev)
-  std::vector<std::pair<BevGeom, uint2*>> occ_tables;
+  std::vector<std::pair<BevGeom, uint4*>> occ_tables;
 
   // ---- multi-GPU gather
   int8_t* gather_base = nullptr;
@@ -854,8 +854,8 @@ int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int 
   for (auto& kv : c->occ_tables)
     if (memcmp(&kv.first, &key, sizeof key) == 0) { g.table = kv.second; return BC_OK; }
   CU(cudaSetDevice(c->device));
-  uint2* d = nullptr;
-  CU(cudaMalloc(&d, (size_t)25 * Hc * Wc * sizeof(uint2)));
+  uint4* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)25 * Hc * Wc * sizeof(uint4)));
   launch_occ_table(key, d, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { cudaFree(d); return fail(c, BC_ERR_CUDA, std::string("occupancy table: ") + cudaGetErrorString(e)); }

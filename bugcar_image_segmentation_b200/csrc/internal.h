@@ -57,7 +57,7 @@ struct BevGeom {            // kernel parameter block for K9 (passed by value)
   int Wc, Hc;               // grid cells
   int binary, ros_layout;
   double ifx, ify;          // nearest-resize source step (cv::resize INTER_NEAREST, fp64)
-  const uint2* table;       // device table of k_occ_table for this geometry ([25][Hc*Wc]); host-side cache key has it null
+  const uint4* table;       // device table of k_occ_table for this geometry ([25][Hc*Wc]); host-side cache key has it null
 };
 
 // ------------------------------------------------------------------ launchers (enet_simt.cu)
@@ -125,7 +125,7 @@ void launch_preprocess(const uint8_t* bgr256, int B, void* out, int out_f64, con
                        cudaStream_t s);
 void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lut256& lut,
                        uint8_t* labels, cudaStream_t s);
-void launch_occ_table(const BevGeom& g, uint2* table, cudaStream_t s);     // [25][Hc*Wc] entries, once per geometry
+void launch_occ_table(const BevGeom& g, uint4* table, cudaStream_t s);     // [25][Hc*Wc] entries, once per geometry
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s);   // needs g.table
 
 }  // namespace bc

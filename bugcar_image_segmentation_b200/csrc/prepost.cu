@@ -122,12 +122,14 @@ void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lu
 // (calibration, grid request) into a table; the per-frame kernel is then a pure integer
 // gather + blend + bit logic on the label bytes.
 //
-// Table entry (8 bytes) for cell `c`, neighbourhood position `pos = j*5+i` (template pixel
+// Table entry (16 bytes) for cell `c`, neighbourhood position `pos = j*5+i` (template pixel
 // (ty-2+j, tx-2+i)), stored [pos][cell] so that a warp reads it coalesced:
-//   .x = sx (int16) | sy (int16) << 16      top-left source pixel of the bilinear footprint
-//   .y = ax | ay << 8 | flags << 16         5-bit fractions; flag 1 = inside the template,
-//                                           flag 2 = inside the pasted crop (else the value is 0)
-
+//   .x = offset of the (clamped) top-left source pixel of the bilinear footprint in the label map
+//   .y = w00 | w01 << 16, .z = w10 | w11 << 16     tap weights wy*wx (0..1024); a tap outside the
+//                                                  label map (BORDER_CONSTANT 0), a pixel outside the
+//                                                  pasted crop or outside the template: weight 0
+//   .w = bit 0: +1 reaches the right tap, bit 1: +cols reaches the lower tap (0 when clamped),
+//        bit 2: inside the template
 // Fixed-point source coordinates of warped pixel (x, y): OpenCV's warpPerspective,
 // INTER_LINEAR, 5-bit fractions.  The fp64 association (block origin xb) and the absence of
 // FMA contraction reproduce WarpPerspectiveInvoker exactly (oracle/cv_ops.py warp_coords_fixed).
@@ -148,7 +150,7 @@ __device__ __forceinline__ void warp_coords(const BevGeom& g, int x, int y, int&
 }
 
 __global__ void __launch_bounds__(128)
-k_occ_table(const BevGeom g, uint2* __restrict__ table) {
+k_occ_table(const BevGeom g, uint4* __restrict__ table) {
   const int cells = g.Hc * g.Wc;
   int cell = blockIdx.x * blockDim.x + threadIdx.x;
   int pos = blockIdx.y;
@@ -158,52 +160,46 @@ k_occ_table(const BevGeom g, uint2* __restrict__ table) {
   int tx = min((int)floor(__dmul_rn((double)cx, g.ifx)), g.occ_w_px - 1);
   int ty = min((int)floor(__dmul_rn((double)cy, g.ify)), g.occ_h_px - 1);
   int x = tx - 2 + pos % 5, y = ty - 2 + pos / 5;
-  uint2 e = make_uint2(0u, 0u);
+  uint4 e = make_uint4(0u, 0u, 0u, 0u);
   if (x >= 0 && x < g.occ_w_px && y >= 0 && y < g.occ_h_px) {
-    unsigned flags = 1;
+    e.w = 4;
     // crop of the warped image pasted into a zero template (bev.py:183-195)
     int px = x - g.gl, py = y - g.gt;
     if (px >= 0 && py >= 0 && px < g.crop_w && py < g.crop_h) {
       int X, Y;
       warp_coords(g, px + g.wl, py + g.wt, X, Y);
-      int sx = min(max(X >> 5, -32768), 32767);   // saturate_cast<short>
-      int sy = min(max(Y >> 5, -32768), 32767);
-      e.x = (unsigned)(sx & 0xffff) | ((unsigned)(sy & 0xffff) << 16);
-      e.y = (unsigned)(X & 31) | ((unsigned)(Y & 31) << 8);
-      flags |= 2;
+      const int sx = min(max(X >> 5, -32768), 32767);   // saturate_cast<short>
+      const int sy = min(max(Y >> 5, -32768), 32767);
+      const int ax = X & 31, ay = Y & 31;
+      const int rows = g.in_rows, cols = g.in_cols;
+      const bool vx0 = sx >= 0 && sx < cols, vx1 = sx + 1 >= 0 && sx + 1 < cols;
+      const bool vy0 = sy >= 0 && sy < rows, vy1 = sy + 1 >= 0 && sy + 1 < rows;
+      const int x0 = min(max(sx, 0), cols - 1), x1 = min(max(sx + 1, 0), cols - 1);
+      const int y0 = min(max(sy, 0), rows - 1), y1 = min(max(sy + 1, 0), rows - 1);
+      const unsigned wx0 = vx0 ? 32 - ax : 0, wx1 = vx1 ? ax : 0, wy0 = vy0 ? 32 - ay : 0, wy1 = vy1 ? ay : 0;
+      e.x = (unsigned)(y0 * cols + x0);
+      e.y = (wy0 * wx0) | ((wy0 * wx1) << 16);
+      e.z = (wy1 * wx0) | ((wy1 * wx1) << 16);
+      e.w |= (unsigned)(x1 - x0) | ((unsigned)(y1 - y0) << 1);
     }
-    e.y |= flags << 16;
   }
   table[(size_t)pos * cells + cell] = e;
 }
 
-void launch_occ_table(const BevGeom& g, uint2* table, cudaStream_t s) {
+void launch_occ_table(const BevGeom& g, uint4* table, cudaStream_t s) {
   dim3 grid((g.Hc * g.Wc + 127) / 128, 25);
   k_occ_table<<<grid, 128, 0, s>>>(g, table);
 }
 
-// (labels + 1) blended at the table entry's footprint: (sum p * wy * wx + 512) >> 10, taps
-// outside the label map contribute 0 (BORDER_CONSTANT), np.add(segmap, 1) wraps in uint8.
-__device__ __forceinline__ int occ_sample(const uint8_t* __restrict__ lab, uint2 e, int rows, int cols) {
-  if (!(e.y & (2u << 16))) return 0;
-  int sx = (int)(short)(e.x & 0xffff), sy = (int)(short)(e.x >> 16);
-  int ax = e.y & 31, ay = (e.y >> 8) & 31;
-  int acc = 0;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    int yy = sy + j;
-    int wy = j ? ay : 32 - ay;
-    if (yy < 0 || yy >= rows) continue;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      int xx = sx + i;
-      int wx = i ? ax : 32 - ax;
-      if (xx < 0 || xx >= cols) continue;
-      int v = (lab[yy * cols + xx] + 1) & 255;   // np.add(segmap, 1) on uint8 (bev.py:177)
-      acc += v * wy * wx;
-    }
-  }
-  return (acc + 512) >> 10;
+// (labels + 1) blended at the table entry's footprint: (sum p * w + 512) >> 10;
+// np.add(segmap, 1) wraps in uint8 (bev.py:177)
+__device__ __forceinline__ int occ_sample(const uint8_t* __restrict__ lab, uint4 e, int cols) {
+  const uint8_t* p0 = lab + e.x;
+  const uint8_t* p1 = p0 + ((e.w & 2) ? cols : 0);
+  const unsigned dx = e.w & 1;
+  unsigned acc = ((p0[0] + 1u) & 255u) * (e.y & 0xffffu) + ((p0[dx] + 1u) & 255u) * (e.y >> 16) +
+                 ((p1[0] + 1u) & 255u) * (e.z & 0xffffu) + ((p1[dx] + 1u) & 255u) * (e.z >> 16);
+  return (int)((acc + 512u) >> 10);
 }
 
 __device__ __forceinline__ bool is_occ(int v, int binary) {
@@ -216,21 +212,24 @@ __device__ __forceinline__ bool is_occ(int v, int binary) {
 // is a speck:
 //   opened(p) = OR_{q in N3(p)} AND_{r in N3(q)} occ(r)   (erode ignores pixels outside
 //   the template, dilate treats them as 0 -- OpenCV default border values)
+// evaluated lazily: q = p needs only the inner 3x3 ring; the outer ring of the 5x5 block is
+// sampled only when that fails (the interior of an occupied region never gets there).
 static constexpr int OCC_FRAMES = 8;
+static constexpr unsigned OCC_INNER = (7u << 6) | (7u << 11) | (7u << 16);     // 3x3 block around bit 12
 
 __global__ void __launch_bounds__(128)
 k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __restrict__ grids) {
-  const uint2* __restrict__ table = g.table;
-  __shared__ uint2 tab[25][128];
+  extern __shared__ uint4 tab[];                  // [25][128]
+  const uint4* __restrict__ table = g.table;
   const int cells = g.Hc * g.Wc;
   const int cell = blockIdx.x * 128 + threadIdx.x;
   const bool live = cell < cells;
   unsigned inside = 0;
 #pragma unroll
   for (int pos = 0; pos < 25; ++pos) {
-    uint2 e = live ? table[(size_t)pos * cells + cell] : make_uint2(0u, 0u);
-    tab[pos][threadIdx.x] = e;
-    if (e.y & (1u << 16)) inside |= 1u << pos;
+    uint4 e = live ? table[(size_t)pos * cells + cell] : make_uint4(0u, 0u, 0u, 0u);
+    tab[pos * 128 + threadIdx.x] = e;
+    if (e.w & 4u) inside |= 1u << pos;
   }
   if (!live) return;               // each thread reads back only its own column: no barrier needed
   const int cx = cell % g.Wc, cy = cell / g.Wc;
@@ -240,29 +239,37 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
   const int n1 = min(B, (int)(blockIdx.y + 1) * OCC_FRAMES);
   for (int n = blockIdx.y * OCC_FRAMES; n < n1; ++n) {
     const uint8_t* lab = labels + (size_t)n * rows * cols;
-    int v = occ_sample(lab, tab[12][threadIdx.x], rows, cols);
+    int v = occ_sample(lab, tab[12 * 128 + threadIdx.x], cols);
     if (is_occ(v, g.binary)) {
       // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i)
       unsigned occ = 1u << 12;
-      for (int pos = 0; pos < 25; ++pos) {
-        if (pos == 12 || !(inside & (1u << pos))) continue;
-        if (is_occ(occ_sample(lab, tab[pos][threadIdx.x], rows, cols), g.binary)) occ |= 1u << pos;
+#pragma unroll
+      for (int pos = 6; pos <= 18; ++pos) {
+        if (!((OCC_INNER >> pos) & 1u) || pos == 12) continue;
+        if ((inside >> pos) & 1u)
+          if (is_occ(occ_sample(lab, tab[pos * 128 + threadIdx.x], cols), g.binary)) occ |= 1u << pos;
       }
-      bool opened = false;
-#pragma unroll
-      for (int qj = 1; qj <= 3; ++qj)
-#pragma unroll
-        for (int qi = 1; qi <= 3; ++qi) {
-          unsigned qbit = 1u << (qj * 5 + qi);
-          if (!(inside & qbit)) continue;            // dilate: outside contributes 0
-          unsigned nb = 0;
-#pragma unroll
-          for (int rj = -1; rj <= 1; ++rj)
-#pragma unroll
-            for (int ri = -1; ri <= 1; ++ri) nb |= 1u << ((qj + rj) * 5 + (qi + ri));
-          // erode: every in-template neighbour must be occupied
-          if (((~occ) & inside & nb) == 0) opened = true;
+      bool opened = ((~occ) & inside & OCC_INNER) == 0;         // q = p: every in-template neighbour occupied
+      if (!opened) {
+        for (int pos = 0; pos < 25; ++pos) {
+          if (((OCC_INNER >> pos) & 1u) || !((inside >> pos) & 1u)) continue;
+          if (is_occ(occ_sample(lab, tab[pos * 128 + threadIdx.x], cols), g.binary)) occ |= 1u << pos;
         }
+#pragma unroll
+        for (int qj = 1; qj <= 3; ++qj)
+#pragma unroll
+          for (int qi = 1; qi <= 3; ++qi) {
+            unsigned qbit = 1u << (qj * 5 + qi);
+            if (!(inside & qbit)) continue;            // dilate: outside contributes 0
+            unsigned nb = 0;
+#pragma unroll
+            for (int rj = -1; rj <= 1; ++rj)
+#pragma unroll
+              for (int ri = -1; ri <= 1; ++ri) nb |= 1u << ((qj + rj) * 5 + (qi + ri));
+            // erode: every in-template neighbour must be occupied
+            if (((~occ) & inside & nb) == 0) opened = true;
+          }
+      }
       if (!opened) v = 2;                             // bev.py:203-205
     }
     int out;
@@ -278,8 +285,14 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
 }
 
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s) {
+  static bool attr_done = false;
+  const int smem = 25 * 128 * (int)sizeof(uint4);   // 51 200 B
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_occgrid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_done = true;
+  }
   dim3 grid((g.Hc * g.Wc + 127) / 128, (B + OCC_FRAMES - 1) / OCC_FRAMES);
-  k_occgrid<<<grid, 128, 0, s>>>(labels, g, B, grids);
+  k_occgrid<<<grid, 128, smem, s>>>(labels, g, B, grids);
 }
 
 }  // namespace bc
