@@ -258,13 +258,30 @@ def main():
                                            pinned_out2[i & 1], stream.cuda_stream)
             model.ctx.pipeline_host_wait(1)
         else:
-            d = dev_sets[0]
-            d.copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
-            pipe.run_device(d, d_grids)
+            # N > 1: the same overlap with torch streams (the NCCL gather sits between the kernels and
+            # the D2H): H2D of step i on the copy stream while step i-1 computes; one step in flight
+            j = i & 1
+            copy_stream.wait_event(computed[j])                 # step i-2 no longer reads this staging buffer
+            with torch.cuda.stream(copy_stream):
+                stage[j].copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
+                copied[j].record(copy_stream)
+            stream.wait_event(copied[j])
+            pipe.run_device(stage[j], d_grids)
+            computed[j].record(stream)
             allg = sharding.gather_grids(d_grids, rank, world)
             if rank == 0:
-                pinned_out.copy_(allg, non_blocking=True)
-            torch.cuda.synchronize()
+                pinned_out2[j].copy_(allg, non_blocking=True)
+            done[j].record(stream)
+            done[j ^ 1].synchronize()                           # step i-1's grids are on the host
+
+    if world > 1:
+        copy_stream = torch.cuda.Stream()
+        stage = [torch.empty_like(dev_sets[0]) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        computed = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        for e in computed + done:
+            e.record(stream)
 
     def timed(fn, steps):
         barrier()

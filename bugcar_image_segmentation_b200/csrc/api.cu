@@ -491,6 +491,8 @@ int upload_net(bc_ctx* c) {
         if (!umma_build(b.um_a, b.cout, cip, nx.ci, b.cin, cw.data(), 9, cb.data(), ca.data(), ew.data(), hb.c3.bias.data(),
                         hb.c3.alpha.data(), hb.alpha_out.data(), nx.c1.w.data(), nx.c1.bias.data(), nx.c1.alpha.data()))
           return fail(c, BC_ERR_CUDA, "building the tcgen05 down-sampling operands failed");
+        if (!down_build(b.um_b, b.cin, b.ci, hb.c1.w.data(), hb.c1.bias.data(), hb.c1.alpha.data()))
+          return fail(c, BC_ERR_CUDA, "building the tcgen05 pooling / strided-conv operands failed");
         continue;
       }
       if (!umma_supported(b)) continue;
@@ -602,11 +604,13 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       bool tc = false;
       if constexpr (std::is_same<T, bf16>::value) tc = c->tensor_cores && c->umma_ready && b.um_a.wblob != nullptr;
       const int cip = tc ? b.um_a.CI : b.ci;       // e1 width as stored (zero-padded to 16 for tcgen05)
-      L(c, "down_pool_conv2x2", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + cip * esz), 2.0 * px * 4 * b.cin * b.ci, s,
-        [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, tc && cip != b.ci, s); });
       if (tc) {
         if constexpr (std::is_same<T, bf16>::value) {
           cudaError_t ce = cudaSuccess;
+          L(c, b.cin == 16 ? "umma_pool_conv16" : "umma_pool_conv64", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + cip * esz),
+            2.0 * px * 4 * b.cin * b.ci, s,
+            [&] { ce = launch_umma_down(b.um_b, (const bf16*)X, (bf16*)P, idx, (bf16*)E1, n, H, W, c->num_sms, s); });
+          if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 pooling launch: ") + cudaGetErrorString(ce));
           L(c, b.cout == 64 ? "umma_down64" : "umma_down128", px * (cip + b.cin + b.cout + b.um_a.CN) * esz,
             2.0 * px * (9.0 * b.ci * b.ci + (double)b.ci * b.cout + (double)b.cout * b.um_a.CN), s,
             [&] { ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)P, (bf16*)Y, (bf16*)E2, n, H, W, taps_for(3, 3, 1), 0, 1,
@@ -617,6 +621,8 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
         }
       } else {
         e1_ready = false;
+        L(c, "down_pool_conv2x2", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + b.ci * esz), 2.0 * px * 4 * b.cin * b.ci, s,
+          [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, false, s); });
         conv("down_conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, 1));
         conv("down_expand_add", E2, Y, P, b.cin, b.c3, b.alpha_out, t1);
       }

@@ -434,6 +434,20 @@ bool make_map_rows(CUtensorMap* m, const bf16* base, size_t pixels, int C, int b
              swizzle_for(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 5D window view of a [N][2Ho][2Wo][C] bf16 tensor: dims (C, dx, ox, dy, n*Ho + oy); one box =
+// one window position of `rows` output rows x `box_w` output pixels
+bool make_map_window(CUtensorMap* m, const bf16* base, int N, int Ho, int Wo, int C, int rows, int box_w) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)Wo, 2, (cuuint64_t)N * Ho};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * Wo * C * 2, (cuuint64_t)4 * Wo * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)C, 1, (cuuint32_t)box_w, 1, (cuuint32_t)rows};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle_for(C * 2 >= 128 ? 128 : C * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool umma_available() { return encode_fn() != nullptr; }
 
 bool umma_supported(const Bottleneck& bn) {

@@ -38,7 +38,7 @@ struct Bottleneck {
   int cin, cout, ci, dilation;
   ConvP c1, c2, c2b, c3, cm; // proj / mid / mid-second (asym) / expand / main (up)
   float* alpha_out = nullptr;
-  UmmaPack um_a, um_b;       // um_b: second half (1x5 + expansion) of an asymmetric bottleneck
+  UmmaPack um_a, um_b;       // um_b: second half (1x5 + expansion) of an asymmetric bottleneck; first half (pool + 2x2 conv) of a down-sampling one
 };
 
 struct Taps { int8_t dy[9]; int8_t dx[9]; };
@@ -98,6 +98,12 @@ bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* con
 void umma_free(UmmaPack& p);
 cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n,
                         int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
+
+// First half of a down-sampling bottleneck on tcgen05 (umma_down.cu): max-pool + argmax and the
+// strided 2x2 conv from the same TMA-staged window tiles; e1 is written 16 wide (zero padded)
+bool down_build(UmmaPack& out, int cin, int ci, const float* w, const float* bias, const float* alpha);
+cudaError_t launch_umma_down(const UmmaPack& pk, const bf16* x, bf16* pooled, uint8_t* idx, bf16* e1, int n, int Ho, int Wo,
+                             int num_sms, cudaStream_t s);
 
 // Upsampling bottleneck on tcgen05 (umma_up.cu)
 bool up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const float* bm, const float* w1, const float* b1,

@@ -47,6 +47,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -148,5 +155,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 bool make_map_e1(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI);   // 4D [N][H][W][CI], box = 128 px
 bool make_map_x(CUtensorMap* m, const bf16* base, size_t pixels, int C);           // 2D [px][C], box [128][64]
 bool make_map_rows(CUtensorMap* m, const bf16* base, size_t pixels, int C, int box_px, int sw);   // 2D [px][C], box [box_px][C]
+// 5D view [N*Ho][2][Wo][2][C] of a [N][2Ho][2Wo][C] tensor (2x2 stride-2 windows), box [rows][1][box_w][1][C]
+bool make_map_window(CUtensorMap* m, const bf16* base, int N, int Ho, int Wo, int C, int rows, int box_w);
 
 }  // namespace bc
