@@ -97,6 +97,7 @@ struct bc_ctx {
   std::vector<Bottleneck> blocks;
   float* d_full_w = nullptr;
   uint8_t* d_head_umma = nullptr;     // tcgen05 operand image of the head (bf16 mode, C <= 16)
+  uint8_t* d_init_umma = nullptr;     // tcgen05 operand image of the initial block (bf16 mode)
   // normalisation LUTs (models.py:91): [256][3] RGB order
   float* d_lut32 = nullptr;
   double* d_lut64 = nullptr;
@@ -399,7 +400,8 @@ void free_net(bc_ctx* c) {
   for (Bottleneck& b : c->blocks) { umma_free(b.um_a); umma_free(b.um_b); }
   for (void* p : c->dev_allocs) cudaFree(p);
   if (c->d_head_umma) cudaFree(c->d_head_umma);
-  c->d_head_umma = nullptr;
+  if (c->d_init_umma) cudaFree(c->d_init_umma);
+  c->d_head_umma = c->d_init_umma = nullptr;
   c->dev_allocs.clear();
   c->blocks.clear();
   c->d_init_w = c->d_init_g = c->d_init_b = c->d_init_a = c->d_full_w = nullptr;
@@ -515,6 +517,8 @@ int upload_net(bc_ctx* c) {
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
     }
+    if (!initial_build(&c->d_init_umma, c->h_init_w.data()))
+      return fail(c, BC_ERR_CUDA, "building the tcgen05 initial-block operands failed");
     if (c->num_classes <= 16) {
       std::vector<float> hw(c->h_full_w.size());
       for (size_t i = 0; i < hw.size(); ++i) hw[i] = bf16_round(c->h_full_w[i]);
@@ -581,9 +585,22 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
   T* E2 = (T*)c->bufE2;
   const double esz = sizeof(T);
   const double in_px_bytes = kind == BC_IN_BGR_U8 ? 3.0 : kind == BC_IN_NCHW_F32 ? 12.0 : 24.0;
-  L(c, "initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
-    launch_initial<T>(x, kind, n, X, c->d_init_w, c->d_init_g, c->d_init_b, c->d_init_a, c->d_lut32, s);
-  });
+  bool init_tc = false;
+  if constexpr (std::is_same<T, bf16>::value) init_tc = c->tensor_cores && c->umma_ready && c->d_init_umma;
+  if (init_tc) {
+    if constexpr (std::is_same<T, bf16>::value) {
+      cudaError_t ce = cudaSuccess;
+      L(c, "umma_initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
+        ce = launch_umma_initial(x, kind, n, (bf16*)X, c->d_init_umma, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
+                                 c->h_init_a.data(), c->num_sms, s);
+      });
+      if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 initial-block launch: ") + cudaGetErrorString(ce));
+    }
+  } else {
+    L(c, "initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
+      launch_initial<T>(x, kind, n, X, c->d_init_w, c->d_init_g, c->d_init_b, c->d_init_a, c->d_lut32, s);
+    });
+  }
   int H = 128, W = 256;   // resolution of X
   if (stop_after == -1) { launch_export_nchw<T>(X, dump, n, 16, H, W, s); return BC_OK; }
   int block_index = 0;

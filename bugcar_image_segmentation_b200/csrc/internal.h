@@ -99,6 +99,11 @@ void umma_free(UmmaPack& p);
 cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n,
                         int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
 
+// Initial block on tcgen05 (umma_initial.cu): 3xTF32 implicit GEMM + max-pool + BN + PReLU
+bool initial_build(uint8_t** out, const float* w);
+cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const float* lut,
+                                const float* g, const float* b, const float* a, int num_sms, cudaStream_t s);
+
 // First half of a down-sampling bottleneck on tcgen05 (umma_down.cu): max-pool + argmax and the
 // strided 2x2 conv from the same TMA-staged window tiles; e1 is written 16 wide (zero padded)
 bool down_build(UmmaPack& out, int cin, int ci, const float* w, const float* bias, const float* alpha);

@@ -1,0 +1,235 @@
+// ENet initial block on tcgen05: conv3x3 s2 p1 (3 -> 13, no bias) || maxpool3x3 s2 p1 (3) -> cat
+// -> BN -> PReLU -> bf16 NHWC, with the frame normalisation of ENET.preprocess (models.py:89-91)
+// fused in for uint8 BGR frames.
+//
+// The conv is a GEMM with M = 128 output pixels, K = 27 (padded to 32), N = 13 (padded to 16).
+// The im2col rows are built by the CTA's threads (one output pixel = one A row = one TMEM lane per
+// thread) because the operand is not a plain view of the input: it is LUT-normalised, zero padded
+// AFTER normalisation, and stride 2.  To keep fp32 accuracy on a tensor pipe that reads tf32 the
+// product is split 3 ways: x = xh + xl, w = wh + wl (h = top 19 bits), acc += xh*wh + xl*wh + xh*wl
+// (the dropped xl*wl term is < 2^-20 relative), so results agree with the CUDA-core fp32 kernel to
+// fp32 round-off and all three input kinds (uint8 BGR / fp32 / fp64 NCHW) give identical outputs.
+//
+// A CTA handles one tile at a time; overlap comes from several co-resident CTAs per SM (36 KB of
+// shared memory, 32 TMEM columns each).  Warp 0 issues the MMAs, warps 1-4 build A and run the
+// epilogue.  Semantics: oracle/enet_oracle.py `initial` (the frozen graph the reference runs,
+// models.py:43-44).
+#include "umma_common.cuh"
+
+#include <cstring>
+
+namespace bc {
+
+struct InitParams {
+  int num_tiles;             // B * 128 * 256 / 128
+  const void* x;             // uint8 (B,256,512,3) BGR | float / double (B,3,256,512)
+  bf16* out;                 // (B,128,256,16)
+  const uint8_t* wblob;      // [hi | lo][16 rows][32 k] tf32 (fp32 bit patterns), 128-byte swizzled rows
+  const float* lut;          // [256][3] fp32 normalisation table (RGB order)
+  float f[48];               // BN scale g[16], shift b[16], PReLU slope a[16]
+};
+
+static constexpr int INIT_A = 128 * 128;          // one A tile: 128 rows x 32 tf32
+static constexpr int INIT_W = 16 * 128;           // one B tile: 16 rows x 32 tf32
+static constexpr int INIT_OFF_A = 0;              // A hi, A lo
+static constexpr int INIT_OFF_W = 2 * INIT_A;     // B hi, B lo
+static constexpr int INIT_OFF_LUT = INIT_OFF_W + 2 * INIT_W;
+static constexpr int INIT_OFF_BAR = INIT_OFF_LUT + 768 * 4;
+static constexpr int INIT_SMEM = INIT_OFF_BAR + 64;
+static constexpr int INIT_MINB = 5;
+
+// tf32 x tf32 -> fp32, both operands K-major: c_format F32 (bit 4), a/b_format TF32 = 2 (bits 7, 10)
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(160, INIT_MINB)
+k_umma_initial(const __grid_constant__ InitParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + INIT_OFF_BAR);
+  enum { A_FULL = 0, D_FULL, W_FULL, NBARS };
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
+  float* slut = (float*)(smem + INIT_OFF_LUT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar(A_FULL), 128);
+    mbar_init(bar(D_FULL), 1);
+    mbar_init(bar(W_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar(W_FULL), 2 * INIT_W);
+    bulk_load(sbase + INIT_OFF_W, p.wblob, 2 * INIT_W, bar(W_FULL));
+  }
+  if (KIND == 0)
+    for (int i = tid; i < 768; i += 160) slut[i] = p.lut[i];
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  constexpr uint32_t IDESC = instr_desc_tf32(128, 16);
+  const int OW = 256, OH = 128, IW = 512, IH = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_wait(bar(W_FULL), 0);
+      for (int k = 0; k < T; ++k) {
+        mbar_wait(bar(A_FULL), k & 1);
+        tc_fence_after();
+        // acc = Ah*Wh + Al*Wh + Ah*Wl, K = 32 as four K = 8 steps each
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {
+          const uint32_t a = sbase + INIT_OFF_A + (part == 1 ? INIT_A : 0);
+          const uint32_t b = sbase + INIT_OFF_W + (part == 2 ? INIT_W : 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32(tmem, smem_desc<128>(a + kk * 32), smem_desc<128>(b + kk * 32), IDESC, (part | kk) != 0);
+        }
+        umma_commit(bar(D_FULL));
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int pix = tile * 128 + m;
+      const int ox = pix % OW, oy = (pix / OW) % OH, n = pix / (OW * OH);
+      // ---- im2col row (k = (c*3 + ky)*3 + kx) + the 3-channel max-pool
+      float a[32];
+#pragma unroll
+      for (int i = 27; i < 32; ++i) a[i] = 0.f;
+      float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy - 1 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = 2 * ox - 1 + kx;
+          float v[3] = {0.f, 0.f, 0.f};                            // zero padding (of the normalised image)
+          if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) {
+            if (KIND == 0) {
+              const uint8_t* s = (const uint8_t*)p.x + ((size_t)(n * IH + iy) * IW + ix) * 3;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = slut[s[2 - c] * 3 + c];   // BGR -> RGB, (u/256 - mean)/std
+            } else if (KIND == 1) {
+              const float* s = (const float*)p.x + (size_t)n * 3 * IH * IW + (size_t)iy * IW + ix;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = s[(size_t)c * IH * IW];
+            } else {
+              const double* s = (const double*)p.x + (size_t)n * 3 * IH * IW + (size_t)iy * IW + ix;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) v[c] = (float)s[(size_t)c * IH * IW];   // TF feed cast
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) mx[c] = fmaxf(mx[c], v[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) a[(c * 3 + ky) * 3 + kx] = v[c];
+        }
+      }
+      // the previous tile's MMAs have finished reading A: this thread passed its D_FULL wait below
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(a[4 * j]) & 0xffffe000u);
+        hi.y = __uint_as_float(__float_as_uint(a[4 * j + 1]) & 0xffffe000u);
+        hi.z = __uint_as_float(__float_as_uint(a[4 * j + 2]) & 0xffffe000u);
+        hi.w = __uint_as_float(__float_as_uint(a[4 * j + 3]) & 0xffffe000u);
+        lo = make_float4(a[4 * j] - hi.x, a[4 * j + 1] - hi.y, a[4 * j + 2] - hi.z, a[4 * j + 3] - hi.w);
+        const uint32_t off = swz<128>((uint32_t)(m * 128 + j * 16));
+        *reinterpret_cast<float4*>(smem + INIT_OFF_A + off) = hi;
+        *reinterpret_cast<float4*>(smem + INIT_OFF_A + INIT_A + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(A_FULL));
+      // ---- epilogue: BN + PReLU on the 13 conv channels and the 3 pooled ones
+      mbar_wait(bar(D_FULL), k & 1);
+      tc_fence_after();
+      float r[16];
+      tmem_ld16(tm_lane, r);
+      tc_fence_before();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[13 + c] = mx[c];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) r[o] = prelu_f(fmaf(r[o], p.f[o], p.f[16 + o]), p.f[32 + o]);
+      uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix * 16);
+      o[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+      o[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
+  }
+}
+
+// w: [27][13] ((c*3+ky)*3+kx major), fp32.  B rows = output channels (13 + 3 zero), K = 32.
+bool initial_build(uint8_t** out, const float* w) {
+  std::vector<uint8_t> img(2 * INIT_W, 0);
+  for (int o = 0; o < 13; ++o)
+    for (int k = 0; k < 27; ++k) {
+      float v = w[k * 13 + o];
+      uint32_t u;
+      memcpy(&u, &v, 4);
+      u &= 0xffffe000u;
+      float hi, lo;
+      memcpy(&hi, &u, 4);
+      lo = v - hi;
+      const uint32_t off = swz<128>((uint32_t)(o * 128 + k * 4));
+      memcpy(img.data() + off, &hi, 4);
+      memcpy(img.data() + INIT_W + off, &lo, 4);
+    }
+  if (cudaMalloc(out, img.size()) != cudaSuccess) return false;
+  return cudaMemcpy(*out, img.data(), img.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const float* lut,
+                                const float* g, const float* b, const float* a, int num_sms, cudaStream_t s) {
+  InitParams p{};
+  p.num_tiles = B * 256;
+  p.x = x;
+  p.out = out;
+  p.wblob = wblob;
+  p.lut = lut;
+  memcpy(p.f, g, 64);
+  memcpy(p.f + 16, b, 64);
+  memcpy(p.f + 32, a, 64);
+  const int smem = INIT_SMEM + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_initial<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int ctas = num_sms * INIT_MINB;
+  const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
+  if (kind == 0) k_umma_initial<0><<<grid, 160, smem, s>>>(p);
+  else if (kind == 1) k_umma_initial<1><<<grid, 160, smem, s>>>(p);
+  else k_umma_initial<2><<<grid, 160, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace bc
