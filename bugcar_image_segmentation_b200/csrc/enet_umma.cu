@@ -166,58 +166,62 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // my tiles
   const bool full = !p.conv_only;
 
+  // Service warps run their loops convergently (all 32 lanes) and elect one lane per instruction
+  // inside the asm (umma_common.cuh): no divergence, no per-lane operand recomputation.
+  // Descriptors advance by plain adds: the address field (bits 0-13, 16-byte units) never carries.
   if (warp == 0) {
     // ============================================================ TMA producer (conv taps)
-    if (lane == 0) {
-      if (full)                                          // first NX residual tiles; the rest are
-        for (int k = 0; k < T && k < NX; ++k) {          // requested by the thread that frees a buffer
-          const int tile = blockIdx.x + k * gridDim.x;
-          if constexpr (NARROW) {
-            mbar_expect_tx(bar(S::X_FULL + k), S::RBUF);
-            tma_load_2d(sbase + S::OFF_R + k * S::RBUF, &map_x, 0, tile * 128, bar(S::X_FULL + k));
-          } else {
-            mbar_expect_tx(bar(S::X_FULL + k), S::XBUF);
-            for (int s = 0; s < S::NSUB; ++s)
-              tma_load_2d(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k));
-          }
-        }
-      int slot = 0, round = 0;
-      for (int k = 0; k < T; ++k) {
+    if (full)                                            // first NX residual tiles; the rest are
+      for (int k = 0; k < T && k < NX; ++k) {            // requested by the thread that frees a buffer
         const int tile = blockIdx.x + k * gridDim.x;
-        const int n = tile / p.tiles_per_frame;
-        const int y0 = (tile % p.tiles_per_frame) * p.rows_per_tile;
-        for (int t = 0; t < p.ntaps; ++t) {
-          if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
-          mbar_expect_tx(bar(S::TAP_FULL + slot), S::TAP_BYTES);
-          tma_load_4d(sbase + S::OFF_TAPS + slot * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
-          if (++slot == S::NRING) { slot = 0; ++round; }
+        if constexpr (NARROW) {
+          mbar_expect_tx_e(bar(S::X_FULL + k), S::RBUF);
+          tma_load_2d_e(sbase + S::OFF_R + k * S::RBUF, &map_x, 0, tile * 128, bar(S::X_FULL + k));
+        } else {
+          mbar_expect_tx_e(bar(S::X_FULL + k), S::XBUF);
+          for (int s = 0; s < S::NSUB; ++s)
+            tma_load_2d_e(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k));
         }
       }
+    int slot = 0, round = 0;
+    // (frame, tile-in-frame) of the current tile, advanced without divisions
+    int n = (int)blockIdx.x / p.tiles_per_frame, ty = (int)blockIdx.x % p.tiles_per_frame;
+    const int dn = (int)gridDim.x / p.tiles_per_frame, dty = (int)gridDim.x % p.tiles_per_frame;
+    for (int k = 0; k < T; ++k) {
+      const int y0 = ty * p.rows_per_tile;
+      for (int t = 0; t < p.ntaps; ++t) {
+        if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
+        mbar_expect_tx_e(bar(S::TAP_FULL + slot), S::TAP_BYTES);
+        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
+        if (++slot == S::NRING) { slot = 0; ++round; }
+      }
+      n += dn; ty += dty;
+      if (ty >= p.tiles_per_frame) { ty -= p.tiles_per_frame; ++n; }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer: conv taps -> D1[group]
-    if (lane == 0) {
-      int slot = 0, round = 0;
-      mbar_wait(bar(S::W_FULL), 0);
-      for (int k = 0; k < T; ++k) {
-        const int g = k % NG;
-        if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
-        for (int t = 0; t < p.ntaps; ++t) {
-          mbar_wait(bar(S::TAP_FULL + slot), round & 1);
-          tc_fence_after();
+    const uint64_t dA0 = smem_desc<RB>(sbase + S::OFF_TAPS), dB0 = smem_desc<RB>(sbase + S::OFF_W2);
+    int slot = 0, round = 0;
+    mbar_wait(bar(S::W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int g = k % NG;
+      if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+      for (int t = 0; t < p.ntaps; ++t) {
+        mbar_wait(bar(S::TAP_FULL + slot), round & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < CI / 16; ++kk)
-            umma_bf16(tmem + S::COL_D1 + g * CI, smem_desc<RB>(sbase + S::OFF_TAPS + slot * S::TAP_BYTES + kk * 32),
-                      smem_desc<RB>(sbase + S::OFF_W2 + t * Wt::W2_TAP + kk * 32), IDESC_CONV, (t | kk) != 0);
-          umma_commit(bar(S::TAP_EMPTY + slot));        // slot reusable once these MMAs retire
-          if (++slot == S::NRING) { slot = 0; ++round; }
-        }
-        umma_commit(bar(S::D1_FULL + g));
+        for (int kk = 0; kk < CI / 16; ++kk)
+          umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::TAP_BYTES >> 4) + kk * 2),
+                      dB0 + (uint64_t)(t * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (t | kk) != 0);
+        umma_commit_e(bar(S::TAP_EMPTY + slot));          // slot reusable once these MMAs retire
+        if (++slot == S::NRING) { slot = 0; ++round; }
       }
+      umma_commit_e(bar(S::D1_FULL + g));
     }
   } else if (warp == 2) {
     // ============================================================ MMA issuer: expansion e2 -> D2[group]
-    if (lane == 0 && full) {
+    if (full) {
+      const uint64_t dA0 = smem_desc<RB>(sbase + S::OFF_E2), dB0 = smem_desc<RB>(sbase + S::OFF_W3);
       mbar_wait(bar(S::W_FULL), 0);
       for (int k = 0; k < T; ++k) {
         const int g = k % NG;
@@ -225,25 +229,26 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_bf16(tmem + S::COL_D2 + g * C, smem_desc<RB>(sbase + S::OFF_E2 + g * S::TAP_BYTES + kk * 32),
-                    smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), IDESC_EXP, kk != 0);
-        umma_commit(bar(S::D2_FULL + g));
+          umma_bf16_e(tmem + S::COL_D2 + g * C, dA0 + (uint64_t)(g * (S::TAP_BYTES >> 4) + kk * 2), dB0 + (uint64_t)(kk * 2),
+                      IDESC_EXP, kk != 0);
+        umma_commit_e(bar(S::D2_FULL + g));
       }
     }
   } else if (warp == 3) {
     // ============================================================ MMA issuer: next projection y -> D3[group]
-    if (lane == 0 && full && p.has_next) {
+    if (full && p.has_next) {
+      const uint64_t dA0 = smem_desc<128>(sbase + S::OFF_X), dB0 = smem_desc<128>(sbase + S::OFF_W1);
       mbar_wait(bar(S::W_FULL), 0);
       for (int k = 0; k < T; ++k) {
         const int g = k % NG;
-        const uint32_t xs = sbase + S::OFF_X + (NARROW ? g : k % NX) * S::XBUF;
+        const uint32_t xo = (uint32_t)(NARROW ? g : k % NX) * (S::XBUF >> 4);
         mbar_wait(bar(S::Y_FULL + g), (k / NG) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < C / 16; ++kk)
-          umma_bf16(tmem + S::COL_D3 + g * CN, smem_desc<128>(xs + (kk / 4) * S::XSUB + (kk % 4) * 32),
-                    smem_desc<128>(sbase + S::OFF_W1 + (kk / 4) * Wt::W1_SUB + (kk % 4) * 32), IDESC_PROJ, kk != 0);
-        umma_commit(bar(S::D3_FULL + g));
+          umma_bf16_e(tmem + S::COL_D3 + g * CN, dA0 + (uint64_t)(xo + (kk / 4) * (S::XSUB >> 4) + (kk % 4) * 2),
+                      dB0 + (uint64_t)((kk / 4) * (Wt::W1_SUB >> 4) + (kk % 4) * 2), IDESC_PROJ, kk != 0);
+        umma_commit_e(bar(S::D3_FULL + g));
       }
     }
   } else {
