@@ -92,34 +92,34 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int k = 0; k < T; ++k) {
-        const int tile = blockIdx.x + k * gridDim.x;
-        if (k >= 1) mbar_wait(bar(TAP_EMPTY), (k - 1) & 1);
-        mbar_expect_tx(bar(TAP_FULL), 4 * S::TAP);
+    {
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      if (k >= 1) mbar_wait(bar(TAP_EMPTY), (k - 1) & 1);
+      mbar_expect_tx_e(bar(TAP_FULL), 4 * S::TAP);
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          tma_load_5d(sbase + S::OFF_TAPS + t * S::TAP, &map_x, 0, t & 1, 0, t >> 1, tile * p.rows_per_tile, bar(TAP_FULL));
-      }
+      for (int t = 0; t < 4; ++t)
+        tma_load_5d_e(sbase + S::OFF_TAPS + t * S::TAP, &map_x, 0, t & 1, 0, t >> 1, tile * p.rows_per_tile, bar(TAP_FULL));
     }
+  }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(bar(W_FULL), 0);
-      for (int k = 0; k < T; ++k) {
-        const int b = k & 1;
-        mbar_wait(bar(TAP_FULL), k & 1);
-        if (k >= 2) mbar_wait(bar(D_EMPTY0 + b), ((k >> 1) - 1) & 1);
-        tc_fence_after();
+    {
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int b = k & 1;
+      mbar_wait(bar(TAP_FULL), k & 1);
+      if (k >= 2) mbar_wait(bar(D_EMPTY0 + b), ((k >> 1) - 1) & 1);
+      tc_fence_after();
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+      for (int t = 0; t < 4; ++t)
 #pragma unroll
-          for (int kk = 0; kk < CIN / 16; ++kk)
-            umma_bf16(tmem + b * 16, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP + kk * 32),
-                      smem_desc<RB>(sbase + S::OFF_W + t * S::WTAP + kk * 32), instr_desc(128, 16), (t | kk) != 0);
-        umma_commit(bar(TAP_EMPTY));
-        umma_commit(bar(D_FULL0 + b));
-      }
+        for (int kk = 0; kk < CIN / 16; ++kk)
+          umma_bf16_e(tmem + b * 16, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP + kk * 32),
+                    smem_desc<RB>(sbase + S::OFF_W + t * S::WTAP + kk * 32), instr_desc(128, 16), (t | kk) != 0);
+      umma_commit_e(bar(TAP_EMPTY));
+      umma_commit_e(bar(D_FULL0 + b));
     }
+  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;

@@ -69,35 +69,35 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int k = 0; k < T; ++k) {
-        const int tile = blockIdx.x + k * gridDim.x;
-        const int n = tile >> 8, y = (tile & 255) >> 1, x0 = (tile & 1) * 128;
-        const int b = k & 1;
-        if (k >= 2) mbar_wait(bar(TAP_EMPTY0 + b), ((k >> 1) - 1) & 1);
-        mbar_expect_tx(bar(TAP_FULL0 + b), 4 * HEAD_TAP);
+    {
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int n = tile >> 8, y = (tile & 255) >> 1, x0 = (tile & 1) * 128;
+      const int b = k & 1;
+      if (k >= 2) mbar_wait(bar(TAP_EMPTY0 + b), ((k >> 1) - 1) & 1);
+      mbar_expect_tx_e(bar(TAP_FULL0 + b), 4 * HEAD_TAP);
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          tma_load_4d(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP, &map_x, 0, x0 + (t & 1), y + (t >> 1), n,
-                      bar(TAP_FULL0 + b));
-      }
+      for (int t = 0; t < 4; ++t)
+        tma_load_4d_e(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP, &map_x, 0, x0 + (t & 1), y + (t >> 1), n,
+                    bar(TAP_FULL0 + b));
     }
+  }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(bar(W_FULL), 0);
-      for (int k = 0; k < T; ++k) {
-        const int b = k & 1;
-        mbar_wait(bar(TAP_FULL0 + b), (k >> 1) & 1);
-        if (k >= 2) mbar_wait(bar(D_EMPTY0 + b), ((k >> 1) - 1) & 1);
-        tc_fence_after();
+    {
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int b = k & 1;
+      mbar_wait(bar(TAP_FULL0 + b), (k >> 1) & 1);
+      if (k >= 2) mbar_wait(bar(D_EMPTY0 + b), ((k >> 1) - 1) & 1);
+      tc_fence_after();
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          umma_bf16(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP),
-                    smem_desc<32>(sbase + HEAD_OFF_W + t * HEAD_WTAP), IDESC, t != 0);
-        umma_commit(bar(TAP_EMPTY0 + b));
-        umma_commit(bar(D_FULL0 + b));
-      }
+      for (int t = 0; t < 4; ++t)
+        umma_bf16_e(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP),
+                  smem_desc<32>(sbase + HEAD_OFF_W + t * HEAD_WTAP), IDESC, t != 0);
+      umma_commit_e(bar(TAP_EMPTY0 + b));
+      umma_commit_e(bar(D_FULL0 + b));
     }
+  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;

@@ -42,11 +42,13 @@ static constexpr int INIT_MINB = 5;
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// executed by a whole (convergent) warp: one elected lane issues
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred pe, p;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -87,23 +89,23 @@ k_umma_initial(const __grid_constant__ InitParams p) {
   const int OW = 256, OH = 128, IW = 512, IH = 256;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_wait(bar(W_FULL), 0);
-      for (int k = 0; k < T; ++k) {
-        mbar_wait(bar(A_FULL), k & 1);
-        tc_fence_after();
-        // acc = Ah*Wh + Al*Wh + Ah*Wl, K = 32 as four K = 8 steps each
+    {
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      mbar_wait(bar(A_FULL), k & 1);
+      tc_fence_after();
+      // acc = Ah*Wh + Al*Wh + Ah*Wl, K = 32 as four K = 8 steps each
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          const uint32_t a = sbase + INIT_OFF_A + (part == 1 ? INIT_A : 0);
-          const uint32_t b = sbase + INIT_OFF_W + (part == 2 ? INIT_W : 0);
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t a = sbase + INIT_OFF_A + (part == 1 ? INIT_A : 0);
+        const uint32_t b = sbase + INIT_OFF_W + (part == 2 ? INIT_W : 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_tf32(tmem, smem_desc<128>(a + kk * 32), smem_desc<128>(b + kk * 32), IDESC, (part | kk) != 0);
-        }
-        umma_commit(bar(D_FULL));
+        for (int kk = 0; kk < 4; ++kk)
+          umma_tf32(tmem, smem_desc<128>(a + kk * 32), smem_desc<128>(b + kk * 32), IDESC, (part | kk) != 0);
       }
+      umma_commit_e(bar(D_FULL));
     }
+  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;

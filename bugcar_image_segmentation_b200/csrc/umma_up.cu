@@ -105,65 +105,65 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
   const int Wh = 2 * p.Wl;                              // high-res width
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int k = 0; k < T; ++k) {
-        const int tile = blockIdx.x + k * gridDim.x;
-        const int b = k & 1;
-        if (k >= 2) mbar_wait(bar(X_EMPTY0 + b), ((k >> 1) - 1) & 1);
-        mbar_expect_tx(bar(X_FULL0 + b), S::XBUF);
-        for (int s = 0; s < S::NSUB; ++s)
-          tma_load_2d(sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + b));
-      }
+    {
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int b = k & 1;
+      if (k >= 2) mbar_wait(bar(X_EMPTY0 + b), ((k >> 1) - 1) & 1);
+      mbar_expect_tx_e(bar(X_FULL0 + b), S::XBUF);
+      for (int s = 0; s < S::NSUB; ++s)
+        tma_load_2d_e(sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + b));
     }
+  }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(bar(W_FULL), 0);
-      for (int k = 0; k < T; ++k) {
-        const int b = k & 1;
-        // G1: [main | e1] = x * B1^T
-        mbar_wait(bar(X_FULL0 + b), (k >> 1) & 1);
-        if (k >= 1) mbar_wait(bar(OUT_FULL), (k - 1) & 1);       // epilogue done reading main of tile k-1
-        tc_fence_after();
+    {
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int b = k & 1;
+      // G1: [main | e1] = x * B1^T
+      mbar_wait(bar(X_FULL0 + b), (k >> 1) & 1);
+      if (k >= 1) mbar_wait(bar(OUT_FULL), (k - 1) & 1);       // epilogue done reading main of tile k-1
+      tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < CIN / 16; ++kk)
-          umma_bf16(tmem + S::COL_A, smem_desc<128>(sbase + S::OFF_X + b * S::XBUF + (kk / 4) * S::XSUB + (kk % 4) * 32),
-                    smem_desc<128>(sbase + S::OFF_B1 + (kk / 4) * S::B1_SUB + (kk % 4) * 32), instr_desc(128, S::N1), kk != 0);
-        umma_commit(bar(X_EMPTY0 + b));
-        umma_commit(bar(DA_FULL));
-        // G2: the four transposed-conv taps
-        mbar_wait(bar(E1_FULL), k & 1);
-        tc_fence_after();
+      for (int kk = 0; kk < CIN / 16; ++kk)
+        umma_bf16_e(tmem + S::COL_A, smem_desc<128>(sbase + S::OFF_X + b * S::XBUF + (kk / 4) * S::XSUB + (kk % 4) * 32),
+                  smem_desc<128>(sbase + S::OFF_B1 + (kk / 4) * S::B1_SUB + (kk % 4) * 32), instr_desc(128, S::N1), kk != 0);
+      umma_commit_e(bar(X_EMPTY0 + b));
+      umma_commit_e(bar(DA_FULL));
+      // G2: the four transposed-conv taps
+      mbar_wait(bar(E1_FULL), k & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < CI / 16; ++kk)
+        umma_bf16_e(tmem + S::COL_B, smem_desc<RB>(sbase + S::OFF_E1 + kk * 32), smem_desc<RB>(sbase + S::OFF_WT + kk * 32),
+                  instr_desc(128, 4 * CI), kk != 0);
+      umma_commit_e(bar(DB_FULL));
+      // G3: expansion of every tap
+      mbar_wait(bar(E2_FULL), k & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_bf16(tmem + S::COL_B, smem_desc<RB>(sbase + S::OFF_E1 + kk * 32), smem_desc<RB>(sbase + S::OFF_WT + kk * 32),
-                    instr_desc(128, 4 * CI), kk != 0);
-        umma_commit(bar(DB_FULL));
-        // G3: expansion of every tap
-        mbar_wait(bar(E2_FULL), k & 1);
-        tc_fence_after();
+          umma_bf16_e(tmem + S::COL_C + t * COUT, smem_desc<RB>(sbase + S::OFF_E2 + t * S::E_TILE + kk * 32),
+                    smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), instr_desc(128, COUT), kk != 0);
+      umma_commit_e(bar(DC_FULL));
+      // G4: next block's projection on the staged high-res rows (COUT == 64: one row = one M tile)
+      if constexpr (COUT == 64) {
+        if (p.has_next) {
+          mbar_wait(bar(OUT_FULL), k & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int kk = 0; kk < CI / 16; ++kk)
-            umma_bf16(tmem + S::COL_C + t * COUT, smem_desc<RB>(sbase + S::OFF_E2 + t * S::E_TILE + kk * 32),
-                      smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), instr_desc(128, COUT), kk != 0);
-        umma_commit(bar(DC_FULL));
-        // G4: next block's projection on the staged high-res rows (COUT == 64: one row = one M tile)
-        if constexpr (COUT == 64) {
-          if (p.has_next) {
-            mbar_wait(bar(OUT_FULL), k & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                umma_bf16(tmem + S::COL_D + r * 16, smem_desc<128>(sbase + S::OFF_OUT + r * S::OUT_ROW + kk * 32),
-                          smem_desc<128>(sbase + S::OFF_W1N + kk * 32), instr_desc(128, 16), kk != 0);
-            umma_commit(bar(DD_FULL));
-          }
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_e(tmem + S::COL_D + r * 16, smem_desc<128>(sbase + S::OFF_OUT + r * S::OUT_ROW + kk * 32),
+                        smem_desc<128>(sbase + S::OFF_W1N + kk * 32), instr_desc(128, 16), kk != 0);
+          umma_commit_e(bar(DD_FULL));
         }
       }
     }
+  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
