@@ -459,6 +459,16 @@ int upload_net(bc_ctx* c) {
     if ((r = upload_conv(c, hb.c3, bf, b.c3))) return r;
     if ((r = upload_conv(c, hb.cm, bf, b.cm))) return r;
     if ((r = upload_vec(c, hb.alpha_out, false, &b.alpha_out))) return r;
+    if (hb.kind == 1 && hb.cin == 16 && hb.ci == 4) {      // stage 5: parameters travel by value (simt_stage5.cu)
+      Stage5Params sp;
+      auto wv = [&](float v) { return bf ? bf16_round(v) : v; };      // same operand rounding as upload_conv
+      for (int i = 0; i < 64; ++i) { sp.w1[i] = wv(hb.c1.w[i]); sp.w3[i] = wv(hb.c3.w[i]); }
+      for (int i = 0; i < 144; ++i) sp.w2[i] = wv(hb.c2.w[i]);
+      for (int i = 0; i < 4; ++i) { sp.b1[i] = hb.c1.bias[i]; sp.a1[i] = hb.c1.alpha[i]; sp.b2[i] = hb.c2.bias[i]; sp.a2[i] = hb.c2.alpha[i]; }
+      for (int i = 0; i < 16; ++i) { sp.b3[i] = hb.c3.bias[i]; sp.a3[i] = hb.c3.alpha[i]; sp.aout[i] = hb.alpha_out[i]; }
+      b.s5.resize(sizeof sp / sizeof(float));
+      memcpy(b.s5.data(), &sp, sizeof sp);
+    }
     c->blocks.push_back(b);
   }
   // tcgen05 operand packs (bf16 mode): conv (+ expansion + the NEXT block's projection)

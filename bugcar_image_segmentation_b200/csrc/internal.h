@@ -38,7 +38,16 @@ struct Bottleneck {
   int cin, cout, ci, dilation;
   ConvP c1, c2, c2b, c3, cm; // proj / mid / mid-second (asym) / expand / main (up)
   float* alpha_out = nullptr;
+  std::vector<float> s5;     // Stage5Params image (host) when the block is the 16-channel regular bottleneck
   UmmaPack um_a, um_b;       // um_b: second half (1x5 + expansion) of an asymmetric bottleneck; first half (pool + 2x2 conv) of a down-sampling one
+};
+
+// stage-5 bottleneck (16 channels, internal width 4): every parameter by value (simt_stage5.cu)
+struct Stage5Params {
+  float w1[64], b1[4], a1[4];      // projection [16][4]
+  float w2[144], b2[4], a2[4];     // 3x3 conv [9][4][4]
+  float w3[64], b3[16], a3[16];    // expansion [4][16]
+  float aout[16];
 };
 
 struct Taps { int8_t dy[9]; int8_t dx[9]; };

@@ -12,29 +12,22 @@
 // (the frozen graph the reference runs, models.py:43-44).
 #include "simt_common.cuh"
 
+#include <cstring>
+
 namespace bc {
 
 static constexpr int S5_TW = 32, S5_TH = 8;                     // pixels per block: 32 x 8, 2 per thread
 static constexpr int S5_HW = S5_TW + 2, S5_HH = S5_TH + 2;      // with halo
 
-struct Stage5Params {
-  const float *w1, *b1, *a1;     // [16][4], [4], [4]
-  const float *w2, *b2, *a2;     // [9][4][4], [4], [4]
-  const float *w3, *b3, *a3;     // [4][16], [16], [16]
-  const float* aout;             // [16]
-};
+// All 336 weights / biases / slopes travel BY VALUE as kernel parameters: with every loop unrolled
+// their indices are compile-time constants, so each one is a constant-bank operand of its FFMA
+// (the kernel was shared-memory-pipe bound, 93 % l1tex, when it fetched them with LDS).
 
 template <typename T>
 __global__ void __launch_bounds__(128)
-k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, Stage5Params p, int H, int W) {
+k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ Stage5Params p, int H, int W) {
   __shared__ float4 se1[S5_HH * S5_HW];        // e1 of the tile + halo, 4 channels per pixel
-  __shared__ float sw1[64], sw2[144], sw3[64], sb[4 + 4 + 4 + 4 + 16 + 16 + 16];
   const int tid = threadIdx.x;
-  if (tid < 64) { sw1[tid] = p.w1[tid]; sw3[tid] = p.w3[tid]; }
-  for (int i = tid; i < 144; i += 128) sw2[i] = p.w2[i];
-  if (tid < 4) { sb[tid] = p.b1[tid]; sb[4 + tid] = p.a1[tid]; sb[8 + tid] = p.b2[tid]; sb[12 + tid] = p.a2[tid]; }
-  if (tid < 16) { sb[16 + tid] = p.b3[tid]; sb[32 + tid] = p.a3[tid]; sb[48 + tid] = p.aout[tid]; }
-  __syncthreads();
   const int x0 = blockIdx.x * S5_TW, y0 = blockIdx.y * S5_TH;
   const T* xf = x + (size_t)blockIdx.z * H * W * 16;
   T* yf = y + (size_t)blockIdx.z * H * W * 16;
@@ -47,15 +40,13 @@ k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, Stage5Params p, 
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
       float v[16];
       ld_ch<16>(xf + ((size_t)gy * W + gx) * 16, v);
-      float a[4] = {sb[0], sb[1], sb[2], sb[3]};
+      float a[4] = {p.b1[0], p.b1[1], p.b1[2], p.b1[3]};
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float4 wr = *reinterpret_cast<const float4*>(sw1 + 4 * k);
-        a[0] = fmaf(v[k], wr.x, a[0]); a[1] = fmaf(v[k], wr.y, a[1]);
-        a[2] = fmaf(v[k], wr.z, a[2]); a[3] = fmaf(v[k], wr.w, a[3]);
-      }
-      e = make_float4(rnd<T>(prelu(a[0], sb[4])), rnd<T>(prelu(a[1], sb[5])), rnd<T>(prelu(a[2], sb[6])),
-                      rnd<T>(prelu(a[3], sb[7])));
+      for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = fmaf(v[k], p.w1[4 * k + j], a[j]);
+      e = make_float4(rnd<T>(prelu(a[0], p.a1[0])), rnd<T>(prelu(a[1], p.a1[1])), rnd<T>(prelu(a[2], p.a1[2])),
+                      rnd<T>(prelu(a[3], p.a1[3])));
     }
     se1[i] = e;
   }
@@ -67,38 +58,38 @@ k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, Stage5Params p, 
     const int ly = (tid >> 5) + 4 * r, lx = tid & 31;          // a warp covers one tile row: coalesced
     const int gy = y0 + ly, gx = x0 + lx;
     if (gy >= H || gx >= W) continue;
-    float a[4] = {sb[8], sb[9], sb[10], sb[11]};
+    float a[4] = {p.b2[0], p.b2[1], p.b2[2], p.b2[3]};
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4 e = se1[(ly + t / 3) * S5_HW + lx + t % 3];
       const float ev[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 wr = *reinterpret_cast<const float4*>(sw2 + (t * 4 + k) * 4);
-        a[0] = fmaf(ev[k], wr.x, a[0]); a[1] = fmaf(ev[k], wr.y, a[1]);
-        a[2] = fmaf(ev[k], wr.z, a[2]); a[3] = fmaf(ev[k], wr.w, a[3]);
-      }
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = fmaf(ev[k], p.w2[(t * 4 + k) * 4 + j], a[j]);
     }
     float e2[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) e2[j] = rnd<T>(prelu(a[j], sb[12 + j]));
+    for (int j = 0; j < 4; ++j) e2[j] = rnd<T>(prelu(a[j], p.a2[j]));
     float o[16], xr[16];
     ld_ch<16>(xf + ((size_t)gy * W + gx) * 16, xr);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = sb[16 + j];
+    for (int j = 0; j < 16; ++j) o[j] = p.b3[j];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = fmaf(e2[k], sw3[k * 16 + j], o[j]);
+      for (int j = 0; j < 16; ++j) o[j] = fmaf(e2[k], p.w3[k * 16 + j], o[j]);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = prelu(prelu(o[j], sb[32 + j]) + xr[j], sb[48 + j]);
+    for (int j = 0; j < 16; ++j) o[j] = prelu(prelu(o[j], p.a3[j]) + xr[j], p.aout[j]);
     st_ch<16>(yf + ((size_t)gy * W + gx) * 16, o);
   }
 }
 
 template <typename T>
 void launch_stage5(const T* x, T* y, const Bottleneck& b, int B, int H, int W, cudaStream_t s) {
-  Stage5Params p{b.c1.w, b.c1.bias, b.c1.alpha, b.c2.w, b.c2.bias, b.c2.alpha, b.c3.w, b.c3.bias, b.c3.alpha, b.alpha_out};
+  if (b.s5.size() != sizeof(Stage5Params) / sizeof(float)) return;      // built by the loader (api.cu)
+  Stage5Params p;
+  memcpy(&p, b.s5.data(), sizeof p);
   dim3 grid((W + S5_TW - 1) / S5_TW, (H + S5_TH - 1) / S5_TH, B);
   k_stage5_bottleneck<T><<<grid, 128, 0, s>>>(x, y, p, H, W);
 }
