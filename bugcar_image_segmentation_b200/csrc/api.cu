@@ -97,7 +97,8 @@ struct bc_ctx {
   std::vector<Bottleneck> blocks;
   float* d_full_w = nullptr;
   uint8_t* d_head_umma = nullptr;     // tcgen05 operand image of the head (bf16 mode, C <= 16)
-  uint8_t* d_init_umma = nullptr;     // tcgen05 operand image of the initial block (bf16 mode)
+  uint8_t* d_init_umma = nullptr;     // tcgen05 operand images of the initial block (bf16 mode): float inputs,
+  uint8_t* d_init_umma_u8 = nullptr;  // uint8 frames
   // normalisation LUTs (models.py:91): [256][3] RGB order
   float* d_lut32 = nullptr;
   double* d_lut64 = nullptr;
@@ -401,7 +402,8 @@ void free_net(bc_ctx* c) {
   for (void* p : c->dev_allocs) cudaFree(p);
   if (c->d_head_umma) cudaFree(c->d_head_umma);
   if (c->d_init_umma) cudaFree(c->d_init_umma);
-  c->d_head_umma = c->d_init_umma = nullptr;
+  if (c->d_init_umma_u8) cudaFree(c->d_init_umma_u8);
+  c->d_head_umma = c->d_init_umma = c->d_init_umma_u8 = nullptr;
   c->dev_allocs.clear();
   c->blocks.clear();
   c->d_init_w = c->d_init_g = c->d_init_b = c->d_init_a = c->d_full_w = nullptr;
@@ -527,7 +529,7 @@ int upload_net(bc_ctx* c) {
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
     }
-    if (!initial_build(&c->d_init_umma, c->h_init_w.data()))
+    if (!initial_build(&c->d_init_umma, c->h_init_w.data()) || !initial_build_u8(&c->d_init_umma_u8, c->h_init_w.data()))
       return fail(c, BC_ERR_CUDA, "building the tcgen05 initial-block operands failed");
     if (c->num_classes <= 16) {
       std::vector<float> hw(c->h_full_w.size());
@@ -601,7 +603,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
     if constexpr (std::is_same<T, bf16>::value) {
       cudaError_t ce = cudaSuccess;
       L(c, "umma_initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
-        ce = launch_umma_initial(x, kind, n, (bf16*)X, c->d_init_umma, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
+        ce = launch_umma_initial(x, kind, n, (bf16*)X, c->d_init_umma, c->d_init_umma_u8, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
                                  c->h_init_a.data(), c->num_sms, s);
       });
       if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 initial-block launch: ") + cudaGetErrorString(ce));

@@ -109,9 +109,11 @@ cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16*
                         int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
 
 // Initial block on tcgen05 (umma_initial.cu): 3xTF32 implicit GEMM + max-pool + BN + PReLU
-bool initial_build(uint8_t** out, const float* w);
-cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const float* lut,
-                                const float* g, const float* b, const float* a, int num_sms, cudaStream_t s);
+bool initial_build(uint8_t** out, const float* w);        // fp32 / fp64 NCHW inputs: 3xTF32
+bool initial_build_u8(uint8_t** out, const float* w);     // uint8 BGR frames: raw bytes + validity columns, bf16 limbs
+cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const uint8_t* wblob_u8,
+                                const float* lut, const float* g, const float* b, const float* a, int num_sms,
+                                cudaStream_t s);
 
 // First half of a down-sampling bottleneck on tcgen05 (umma_down.cu): max-pool + argmax and the
 // strided 2x2 conv from the same TMA-staged window tiles; e1 is written 16 wide (zero padded)

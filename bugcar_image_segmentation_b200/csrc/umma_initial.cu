@@ -186,6 +186,167 @@ k_umma_initial(const __grid_constant__ InitParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// uint8 frames: the normalisation is affine, v = s_c * u + t_c with s_c = 1 / (256 std_c) and
+// t_c = -mean_c / std_c (models.py:17-18,91), so
+//     sum_k w_k v_k = sum_k (w_k s_c) u_k + sum_taps valid(tap) * (sum_c w_(c,tap) t_c)
+// where valid(tap) = 0 for taps in the zero padding (the conv pads the NORMALISED image).  The A
+// operand is then the RAW bytes (exact in bf16) plus nine 0/1 validity columns: no lookup table, no
+// fp32 operand split on the activation side (4x less shared-memory traffic than the tf32 form);
+// the folded weights carry their full fp32 precision as three bf16 limbs.  K = 27 + 9, padded to 64.
+static constexpr int U8_A = 128 * 128;            // A tile: 128 rows x 64 bf16
+static constexpr int U8_W = 16 * 128;             // one limb of B: 16 rows x 64 bf16
+static constexpr int U8_OFF_A = 0;
+static constexpr int U8_OFF_W = U8_A;
+static constexpr int U8_OFF_BAR = U8_OFF_W + 3 * U8_W;
+static constexpr int U8_SMEM = U8_OFF_BAR + 64;
+static constexpr int U8_MINB = 6;
+
+__global__ void __launch_bounds__(160, U8_MINB)
+k_umma_initial_u8(const __grid_constant__ InitParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = (uint64_t*)(smem + U8_OFF_BAR);
+  enum { A_FULL = 0, D_FULL, W_FULL, NBARS };
+  auto bar = [&](int i) { return smem_u32(&bars[i]); };
+  uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar(A_FULL), 128);
+    mbar_init(bar(D_FULL), 1);
+    mbar_init(bar(W_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar(W_FULL), 3 * U8_W);
+    bulk_load(sbase + U8_OFF_W, p.wblob, 3 * U8_W, bar(W_FULL));
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  } else {
+    // K columns 40..63 of this thread's A row are never written again: zero them once
+    const int m = (warp & 3) * 32 + lane;
+#pragma unroll
+    for (int j = 5; j < 8; ++j)
+      *reinterpret_cast<uint4*>(smem + U8_OFF_A + swz<128>((uint32_t)(m * 128 + j * 16))) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int OW = 256, OH = 128, IW = 512, IH = 256;
+
+  if (warp == 0) {
+    const uint64_t dA0 = smem_desc<128>(sbase + U8_OFF_A), dB0 = smem_desc<128>(sbase + U8_OFF_W);
+    mbar_wait(bar(W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      mbar_wait(bar(A_FULL), k & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int limb = 0; limb < 3; ++limb)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16_e(tmem, dA0 + (uint64_t)(kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2), instr_desc(128, 16),
+                      (limb | kk) != 0);
+      umma_commit_e(bar(D_FULL));
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int m = q4 * 32 + lane;
+    const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+    for (int k = 0; k < T; ++k) {
+      const int tile = blockIdx.x + k * gridDim.x;
+      const int pix = tile * 128 + m;
+      const int ox = pix % OW, oy = (pix / OW) % OH, n = pix / (OW * OH);
+      // ---- A row: bf16 halves, column (c*3 + ky)*3 + kx = byte of RGB channel c, column 27 + ky*3 + kx = valid
+      uint32_t h[40];                                   // one bf16 per entry (low 16 bits), packed below
+#pragma unroll
+      for (int i = 36; i < 40; ++i) h[i] = 0u;
+      uint32_t mxb[3] = {0u, 0u, 0u};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy - 1 + ky;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = 2 * ox - 1 + kx;
+          const bool ok = iy >= 0 && iy < IH && ix >= 0 && ix < IW;
+          uint32_t u[3] = {0u, 0u, 0u};
+          if (ok) {
+            const uint8_t* s = (const uint8_t*)p.x + ((size_t)(n * IH + iy) * IW + ix) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[c] = s[2 - c];                       // BGR -> RGB
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            mxb[c] = max(mxb[c], u[c]);                                        // valid taps only (others are 0)
+            h[(c * 3 + ky) * 3 + kx] = __float_as_uint((float)u[c]) >> 16;     // exact: u < 256
+          }
+          h[27 + ky * 3 + kx] = ok ? 0x3f80u : 0u;                             // 1.0 / 0.0
+        }
+      }
+      // (the previous tile's MMAs have finished reading A: this thread passed its D_FULL wait below)
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        *reinterpret_cast<uint4*>(smem + U8_OFF_A + swz<128>((uint32_t)(m * 128 + j * 16))) =
+            make_uint4(h[8 * j] | (h[8 * j + 1] << 16), h[8 * j + 2] | (h[8 * j + 3] << 16),
+                       h[8 * j + 4] | (h[8 * j + 5] << 16), h[8 * j + 6] | (h[8 * j + 7] << 16));
+      fence_proxy_async();
+      mbar_arrive(bar(A_FULL));
+      // max-pool of the normalised image = normalisation of the max byte (the map is increasing)
+      float mx[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) mx[c] = __ldg(p.lut + mxb[c] * 3 + c);
+      // ---- epilogue: BN + PReLU on the 13 conv channels and the 3 pooled ones
+      mbar_wait(bar(D_FULL), k & 1);
+      tc_fence_after();
+      float r[16];
+      tmem_ld16(tm_lane, r);
+      tc_fence_before();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[13 + c] = mx[c];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) r[o] = prelu_f(fmaf(r[o], p.f[o], p.f[16 + o]), p.f[32 + o]);
+      uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix * 16);
+      o[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+      o[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32));
+  }
+}
+
+// B image of the uint8 form: three bf16 limbs of  w_k * s_c  (27 columns) and of  sum_c w_(c,tap) * t_c
+// (9 columns), rows = output channels.  w: [27][13] ((c*3+ky)*3+kx major).
+bool initial_build_u8(uint8_t** out, const float* w) {
+  const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18
+  std::vector<uint8_t> img(3 * U8_W, 0);
+  auto put = [&](int o, int col, double v) {
+    for (int limb = 0; limb < 3; ++limb) {
+      __nv_bfloat16 hb = __float2bfloat16_rn((float)v);
+      v -= (double)__bfloat162float(hb);
+      memcpy(img.data() + limb * U8_W + swz<128>((uint32_t)(o * 128 + col * 2)), &hb, 2);
+    }
+  };
+  for (int o = 0; o < 13; ++o) {
+    for (int c = 0; c < 3; ++c)
+      for (int tap = 0; tap < 9; ++tap) put(o, c * 9 + tap, (double)w[(c * 9 + tap) * 13 + o] / (256.0 * sd[c]));
+    for (int tap = 0; tap < 9; ++tap) {
+      double t = 0.0;
+      for (int c = 0; c < 3; ++c) t += (double)w[(c * 9 + tap) * 13 + o] * (-mean[c] / sd[c]);
+      put(o, 27 + tap, t);
+    }
+  }
+  if (cudaMalloc(out, img.size()) != cudaSuccess) return false;
+  return cudaMemcpy(*out, img.data(), img.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
 // w: [27][13] ((c*3+ky)*3+kx major), fp32.  B rows = output channels (13 + 3 zero), K = 32.
 bool initial_build(uint8_t** out, const float* w) {
   std::vector<uint8_t> img(2 * INIT_W, 0);
@@ -206,13 +367,14 @@ bool initial_build(uint8_t** out, const float* w) {
   return cudaMemcpy(*out, img.data(), img.size(), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
-cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const float* lut,
-                                const float* g, const float* b, const float* a, int num_sms, cudaStream_t s) {
+cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const uint8_t* wblob_u8,
+                                const float* lut, const float* g, const float* b, const float* a, int num_sms,
+                                cudaStream_t s) {
   InitParams p{};
   p.num_tiles = B * 256;
   p.x = x;
   p.out = out;
-  p.wblob = wblob;
+  p.wblob = kind == 0 ? wblob_u8 : wblob;
   p.lut = lut;
   memcpy(p.f, g, 64);
   memcpy(p.f + 16, b, 64);
@@ -226,10 +388,14 @@ cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
+  if (kind == 0) {
+    const int ctas8 = num_sms * U8_MINB;
+    k_umma_initial_u8<<<p.num_tiles < ctas8 ? p.num_tiles : ctas8, 160, U8_SMEM + 1024, s>>>(p);
+    return cudaGetLastError();
+  }
   const int ctas = num_sms * INIT_MINB;
   const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  if (kind == 0) k_umma_initial<0><<<grid, 160, smem, s>>>(p);
-  else if (kind == 1) k_umma_initial<1><<<grid, 160, smem, s>>>(p);
+  if (kind == 1) k_umma_initial<1><<<grid, 160, smem, s>>>(p);
   else k_umma_initial<2><<<grid, 160, smem, s>>>(p);
   return cudaGetLastError();
 }
