@@ -651,7 +651,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       } else {
         e1_ready = false;
         L(c, "down_pool_conv2x2", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + b.ci * esz), 2.0 * px * 4 * b.cin * b.ci, s,
-          [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, false, s); });
+          [&] { launch_down_a<T>(X, n, H, W, b.cin, b.ci, P, idx, E1, b.c1, s); });
         conv("down_conv3x3", E1, E2, nullptr, 0, b.c2, nullptr, taps_for(3, 3, 1));
         conv("down_expand_add", E2, Y, P, b.cin, b.c3, b.alpha_out, t1);
       }

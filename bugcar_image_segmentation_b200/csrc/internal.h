@@ -75,10 +75,9 @@ struct Net;   // forward (api.cu)
 template <typename T>
 void launch_initial(const void* x, int kind, int B, T* out, const float* w, const float* g,
                     const float* b, const float* alpha, const float* lut, cudaStream_t s);
-// pad16: write e1 with 16 channels (ci real + zeros), the K granularity of tcgen05
 template <typename T>
 void launch_down_a(const T* x, int B, int H, int W, int cin, int ci, T* pooled, uint8_t* idx,
-                   T* e1, const ConvP& c1, bool pad16, cudaStream_t s);
+                   T* e1, const ConvP& c1, cudaStream_t s);
 template <typename T>
 void launch_conv(const T* in, T* out, const T* res, int res_ch, const ConvP& c,
                  const float* alpha_out, int B, int H, int W, const Taps& taps, cudaStream_t s);

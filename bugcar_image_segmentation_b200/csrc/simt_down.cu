@@ -18,8 +18,7 @@ namespace bc {
 // main: maxpool 2x2 s2 with argmax (2-bit window position, first max wins);
 // ext:  conv 2x2 s2 (CIN->CI) + BN + PReLU.  One thread per half-resolution pixel.
 // H, W are the OUTPUT (half) resolution.
-// CIP >= CI: channels written per e1 pixel (zero padded; the tcgen05 path needs K = 16).
-template <typename T, int CIN, int CI, int CIP>
+template <typename T, int CIN, int CI>
 __global__ void __launch_bounds__(128)
 k_down_a(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ idx,
          T* __restrict__ e1, const float* __restrict__ w, const float* __restrict__ bias,
@@ -62,26 +61,23 @@ k_down_a(const T* __restrict__ x, T* __restrict__ pooled, uint8_t* __restrict__ 
       *reinterpret_cast<uint32_t*>(ip) = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
     }
   }
-  float o[CIP];
 #pragma unroll
-  for (int j = 0; j < CIP; ++j) o[j] = j < CI ? prelu(acc[j < CI ? j : 0], alpha[j < CI ? j : 0]) : 0.f;
-  st_ch<CIP>(e1 + (size_t)p * CIP, o);
+  for (int j = 0; j < CI; ++j) acc[j] = prelu(acc[j], alpha[j]);
+  st_ch<CI>(e1 + (size_t)p * CI, acc);
 }
 
 template <typename T>
 void launch_down_a(const T* x, int B, int H, int W, int cin, int ci, T* pooled, uint8_t* idx,
-                   T* e1, const ConvP& c1, bool pad16, cudaStream_t s) {
+                   T* e1, const ConvP& c1, cudaStream_t s) {
   int total = B * H * W;
   int grid = (total + 127) / 128;
   size_t smem = (size_t)4 * cin * ci * sizeof(float);
-  if (cin == 16 && ci == 4 && pad16)
-    k_down_a<T, 16, 4, 16><<<grid, 128, smem, s>>>(x, pooled, idx, e1, c1.w, c1.bias, c1.alpha, H, W, total);
-  else if (cin == 16 && ci == 4)
-    k_down_a<T, 16, 4, 4><<<grid, 128, smem, s>>>(x, pooled, idx, e1, c1.w, c1.bias, c1.alpha, H, W, total);
+  if (cin == 16 && ci == 4)
+    k_down_a<T, 16, 4><<<grid, 128, smem, s>>>(x, pooled, idx, e1, c1.w, c1.bias, c1.alpha, H, W, total);
   else if (cin == 64 && ci == 16)
-    k_down_a<T, 64, 16, 16><<<grid, 128, smem, s>>>(x, pooled, idx, e1, c1.w, c1.bias, c1.alpha, H, W, total);
+    k_down_a<T, 64, 16><<<grid, 128, smem, s>>>(x, pooled, idx, e1, c1.w, c1.bias, c1.alpha, H, W, total);
 }
-template void launch_down_a<float>(const float*, int, int, int, int, int, float*, uint8_t*, float*, const ConvP&, bool, cudaStream_t);
-template void launch_down_a<bf16>(const bf16*, int, int, int, int, int, bf16*, uint8_t*, bf16*, const ConvP&, bool, cudaStream_t);
+template void launch_down_a<float>(const float*, int, int, int, int, int, float*, uint8_t*, float*, const ConvP&, cudaStream_t);
+template void launch_down_a<bf16>(const bf16*, int, int, int, int, int, bf16*, uint8_t*, bf16*, const ConvP&, cudaStream_t);
 
 }  // namespace bc

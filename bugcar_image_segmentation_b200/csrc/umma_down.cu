@@ -92,7 +92,6 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
-    {
     for (int k = 0; k < T; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
       if (k >= 1) mbar_wait(bar(TAP_EMPTY), (k - 1) & 1);
@@ -101,9 +100,7 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
       for (int t = 0; t < 4; ++t)
         tma_load_5d_e(sbase + S::OFF_TAPS + t * S::TAP, &map_x, 0, t & 1, 0, t >> 1, tile * p.rows_per_tile, bar(TAP_FULL));
     }
-  }
   } else if (warp == 1) {
-    {
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
       const int b = k & 1;
@@ -119,7 +116,6 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
       umma_commit_e(bar(TAP_EMPTY));
       umma_commit_e(bar(D_FULL0 + b));
     }
-  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;

@@ -69,7 +69,6 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0) {
-    {
     for (int k = 0; k < T; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
       const int n = tile >> 8, y = (tile & 255) >> 1, x0 = (tile & 1) * 128;
@@ -81,9 +80,7 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
         tma_load_4d_e(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP, &map_x, 0, x0 + (t & 1), y + (t >> 1), n,
                     bar(TAP_FULL0 + b));
     }
-  }
   } else if (warp == 1) {
-    {
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
       const int b = k & 1;
@@ -97,7 +94,6 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
       umma_commit_e(bar(TAP_EMPTY0 + b));
       umma_commit_e(bar(D_FULL0 + b));
     }
-  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;

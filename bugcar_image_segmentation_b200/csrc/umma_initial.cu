@@ -89,7 +89,6 @@ k_umma_initial(const __grid_constant__ InitParams p) {
   const int OW = 256, OH = 128, IW = 512, IH = 256;
 
   if (warp == 0) {
-    {
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
       mbar_wait(bar(A_FULL), k & 1);
@@ -105,7 +104,6 @@ k_umma_initial(const __grid_constant__ InitParams p) {
       }
       umma_commit_e(bar(D_FULL));
     }
-  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;

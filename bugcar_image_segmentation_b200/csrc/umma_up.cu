@@ -105,7 +105,6 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
   const int Wh = 2 * p.Wl;                              // high-res width
 
   if (warp == 0) {
-    {
     for (int k = 0; k < T; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
       const int b = k & 1;
@@ -114,9 +113,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       for (int s = 0; s < S::NSUB; ++s)
         tma_load_2d_e(sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + b));
     }
-  }
   } else if (warp == 1) {
-    {
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
       const int b = k & 1;
@@ -163,7 +160,6 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
         }
       }
     }
-  }
   } else {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
