@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true")
     ap.add_argument("--weights", default=WEIGHTS, choices=sorted(WEIGHT_FILES))
     ap.add_argument("--frames", default=FRAMES, choices=["scene", "noise"])
     args = ap.parse_args()
@@ -242,7 +243,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: the grids of every rank land in rank 0's buffer through K9's own peer stores
+    # (sharding.PeerGather); --nccl-gather switches back to one NCCL gather per step
+    peer = None
+    if world > 1 and not args.nccl_gather:
+        peer = sharding.PeerGather(model.ctx, rank, world, B, (Hc, Wc), local)
+
     def step_device(i):
+        if peer is not None:
+            peer.use(i)
+            pipe.run_device(dev_sets[i % N_INPUT_SETS], to_gather=True)
+            return peer.ready()
         pipe.run_device(dev_sets[i % N_INPUT_SETS], d_grids)
         if world > 1:
             return sharding.gather_grids(d_grids, rank, world)
@@ -266,9 +277,15 @@ def main():
                 stage[j].copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
                 copied[j].record(copy_stream)
             stream.wait_event(copied[j])
-            pipe.run_device(stage[j], d_grids)
-            computed[j].record(stream)
-            allg = sharding.gather_grids(d_grids, rank, world)
+            if peer is not None:
+                peer.use(i)
+                pipe.run_device(stage[j], to_gather=True)
+                computed[j].record(stream)
+                allg = peer.ready()
+            else:
+                pipe.run_device(stage[j], d_grids)
+                computed[j].record(stream)
+                allg = sharding.gather_grids(d_grids, rank, world)
             if rank == 0:
                 pinned_out2[j].copy_(allg, non_blocking=True)
             done[j].record(stream)
@@ -393,7 +410,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(B),
                        l2=f"{N_INPUT_SETS} input sets x {B * 393216 / 1e6:.0f} MB rotate (> 126 MB L2)",
-                       parallelism=f"frame-sharded dp{world}" + (", grids gathered to rank 0 (NCCL)" if world > 1 else ""),
+                       parallelism=f"frame-sharded dp{world}" + ("" if world == 1 else ", grids gathered to rank 0 (NCCL gather)"
+                                                                 if peer is None else ", grids stored by K9 into rank 0's "
+                                                                 "peer-mapped buffer (NVLink), one barrier per step"),
                        chunk=args.chunk, tensor_cores=not args.no_tc),
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},

@@ -35,11 +35,18 @@ class FramePipeline:
     def grid_shape(self):
         return (self.Wc, self.Hc) if self.ros_layout else (self.Hc, self.Wc)
 
-    def run_device(self, d_frames, d_grids=None, d_labels=None):
+    def run_device(self, d_frames, d_grids=None, d_labels=None, to_gather=False):
         """d_frames: CUDA uint8 (B,h,w,3).  Returns CUDA int8 (B,*grid_shape); asynchronous
-        on the current stream."""
+        on the current stream.  ``to_gather``: write the grids straight into the peer-mapped
+        gather buffer selected with ``sharding.PeerGather.use`` (returns None)."""
         torch = self._torch
         B, h, w, _ = d_frames.shape
+        if to_gather:
+            if B > self.ctx.max_batch:
+                raise ValueError("to_gather needs the batch in one call (B <= max_batch)")
+            self.ctx.pipeline(d_frames, h, w, B, self.lut, self.w_m, self.h_m, self.cell_m, self.binary,
+                              self.ros_layout, d_labels, None, runtime.stream_handle(torch, self.device))
+            return None
         if d_grids is None:
             d_grids = torch.empty((B,) + self.grid_shape, dtype=torch.int8, device=d_frames.device)
         s = runtime.stream_handle(torch, self.device)

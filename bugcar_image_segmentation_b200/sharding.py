@@ -33,3 +33,51 @@ def gather_grids(local, rank, world, backend_device=None):
         if rank == 0:
             out = torch.stack(lst)
     return out.reshape((-1,) + tuple(local.shape[1:])) if rank == 0 else None
+
+
+class PeerGather:
+    """Grids gathered WITHOUT a data collective: rank 0 owns one (world*B, Hc, Wc) int8 buffer, every
+    other rank maps it into its own address space (CUDA IPC -> peer access over NVLink / NVSwitch) and
+    hands the mapping to the library (``bc_gather_setup``), so the occupancy-grid kernel's own stores
+    land in rank 0's memory at ``rank * B`` -- the 'gather' is the tail of K9.  What remains is one
+    barrier per step (``ready()``) so that rank 0 knows every peer's kernel has finished.
+
+    ``slots`` buffers alternate (``use(i)``) so that step i+1 may write while rank 0 still copies
+    step i to the host."""
+
+    def __init__(self, ctx, rank, world, B, grid_shape, device, slots=2):
+        import torch
+        self.torch, self.ctx, self.rank, self.world, self.B = torch, ctx, rank, world, B
+        shape = (world * B,) + tuple(grid_shape)
+        self.bufs = []
+        for _ in range(slots):
+            handle = [None]
+            if rank == 0:
+                buf = torch.empty(shape, dtype=torch.int8, device=f"cuda:{device}")
+                handle = [buf.untyped_storage()._share_cuda_()]
+            dist.broadcast_object_list(handle, src=0)
+            if rank != 0:
+                h = list(handle[0])
+                h[0] = device                                   # open the mapping on THIS rank's device
+                storage = torch.UntypedStorage._new_shared_cuda(*h)
+                buf = torch.empty(0, dtype=torch.int8, device=f"cuda:{device}").set_(storage, 0, shape)
+            self.bufs.append(buf)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=f"cuda:{device}")
+        self.cur = 0
+        self.use(0)
+
+    def use(self, i):
+        """select the buffer the next pipeline call writes to (d_grids = NULL in that call)"""
+        self.cur = i % len(self.bufs)
+        self.ctx.gather_setup(self.bufs[self.cur].data_ptr(), self.rank, self.world)
+
+    def ready(self):
+        """enqueue the barrier on the current stream; on rank 0 returns the full (world*B, ...) tensor,
+        valid for work enqueued on this stream after the call"""
+        # a one-element all-reduce is the barrier: stream ordered, it does not block the host
+        # (dist.barrier() does), so the next step can be enqueued behind it
+        dist.all_reduce(self.flag)
+        return self.bufs[self.cur] if self.rank == 0 else None
+
+    def close(self):
+        self.ctx.gather_setup(None, 0, 1)
