@@ -198,7 +198,7 @@ static constexpr int U8_OFF_A = 0;
 static constexpr int U8_OFF_W = U8_A;
 static constexpr int U8_OFF_BAR = U8_OFF_W + 3 * U8_W;
 static constexpr int U8_SMEM = U8_OFF_BAR + 64;
-static constexpr int U8_MINB = 6;
+static constexpr int U8_MINB = 7;
 
 __global__ void __launch_bounds__(160, U8_MINB)
 k_umma_initial_u8(const __grid_constant__ InitParams p) {
@@ -254,27 +254,54 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
     const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
+    // The 3 x 3 pixel window of an output pixel is 9 contiguous bytes per input row, starting at byte
+    // 6*ox - 3 of the row: fetched as the three aligned 32-bit words that cover them, realigned with
+    // funnel shifts.  ox = 0: the first word would lie before the row; its bytes are padding anyway.
+    // The words of tile k+1 are requested before this thread waits for tile k's accumulator, so the
+    // global-load latency hides behind the MMA round trip.
+    uint32_t w[9];
+    int pix = 0, ox = 0, oy = 0;
+    auto fetch = [&](int k) {
+      pix = ((int)blockIdx.x + k * (int)gridDim.x) * 128 + m;
+      ox = pix % OW;
+      oy = (pix / OW) % OH;
+      const int n = pix / (OW * OH);
+      const int wbase = (6 * ox - 3) & ~3;              // -4 for ox = 0
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy - 1 + ky;
+        w[3 * ky] = w[3 * ky + 1] = w[3 * ky + 2] = 0u;
+        if (iy >= 0 && iy < IH) {
+          const uint8_t* row = (const uint8_t*)p.x + (size_t)(n * IH + iy) * IW * 3;
+          if (wbase >= 0) w[3 * ky] = __ldg(reinterpret_cast<const uint32_t*>(row + wbase));
+          w[3 * ky + 1] = __ldg(reinterpret_cast<const uint32_t*>(row + wbase + 4));
+          w[3 * ky + 2] = __ldg(reinterpret_cast<const uint32_t*>(row + wbase + 8));
+        }
+      }
+    };
+    if (T > 0) fetch(0);
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
-      const int pix = tile * 128 + m;
-      const int ox = pix % OW, oy = (pix / OW) % OH, n = pix / (OW * OH);
       // ---- A row: bf16 halves, column (c*3 + ky)*3 + kx = byte of RGB channel c, column 27 + ky*3 + kx = valid
       uint32_t h[40];                                   // one bf16 per entry (low 16 bits), packed below
 #pragma unroll
       for (int i = 36; i < 40; ++i) h[i] = 0u;
       uint32_t mxb[3] = {0u, 0u, 0u};
+      const int sh = ((6 * ox - 3) & 3) * 8;            // 8 or 24
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int iy = 2 * oy - 1 + ky;
+        const bool rok = iy >= 0 && iy < IH;
+        const uint32_t r0 = __funnelshift_r(w[3 * ky], w[3 * ky + 1], sh), r1 = __funnelshift_r(w[3 * ky + 1], w[3 * ky + 2], sh),
+                       r2 = w[3 * ky + 2] >> sh;        // window bytes 0-3, 4-7, 8
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int ix = 2 * ox - 1 + kx;
-          const bool ok = iy >= 0 && iy < IH && ix >= 0 && ix < IW;
-          uint32_t u[3] = {0u, 0u, 0u};
-          if (ok) {
-            const uint8_t* s = (const uint8_t*)p.x + ((size_t)(n * IH + iy) * IW + ix) * 3;
+          const bool ok = rok && (kx > 0 || ox > 0);    // the window never leaves the row on the right (ix <= 511)
+          uint32_t u[3];                                // RGB from the BGR bytes 3*kx + (2, 1, 0)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) u[c] = s[2 - c];                       // BGR -> RGB
+          for (int c = 0; c < 3; ++c) {
+            const int bi = 3 * kx + 2 - c;
+            const uint32_t word = bi < 4 ? r0 : bi < 8 ? r1 : r2;
+            u[c] = ok ? (word >> (8 * (bi & 3))) & 0xffu : 0u;
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -296,6 +323,8 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       float mx[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) mx[c] = __ldg(p.lut + mxb[c] * 3 + c);
+      const int out_pix = pix;
+      if (k + 1 < T) fetch(k + 1);
       // ---- epilogue: BN + PReLU on the 13 conv channels and the 3 pooled ones
       mbar_wait(bar(D_FULL), k & 1);
       tc_fence_after();
@@ -306,7 +335,7 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       for (int c = 0; c < 3; ++c) r[13 + c] = mx[c];
 #pragma unroll
       for (int o = 0; o < 16; ++o) r[o] = prelu_f(fmaf(r[o], p.f[o], p.f[16 + o]), p.f[32 + o]);
-      uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix * 16);
+      uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)out_pix * 16);
       o[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
       o[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
     }
@@ -372,7 +401,7 @@ cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const
   p.num_tiles = B * 256;
   p.x = x;
   p.out = out;
-  p.wblob = kind == 0 ? wblob_u8 : wblob;
+  p.wblob = (kind == 0 && ((uintptr_t)x & 3) == 0) ? wblob_u8 : wblob;
   p.lut = lut;
   memcpy(p.f, g, 64);
   memcpy(p.f + 16, b, 64);
@@ -386,14 +415,15 @@ cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  if (kind == 0) {
-    const int ctas8 = num_sms * U8_MINB;
+  if (kind == 0 && ((uintptr_t)x & 3) == 0) {          // the byte-window loads are 32-bit: a frame pointer that is not
+    const int ctas8 = num_sms * U8_MINB;               // 4-byte aligned takes the byte-wise tf32 kernel below
     k_umma_initial_u8<<<p.num_tiles < ctas8 ? p.num_tiles : ctas8, 160, U8_SMEM + 1024, s>>>(p);
     return cudaGetLastError();
   }
   const int ctas = num_sms * INIT_MINB;
   const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  if (kind == 1) k_umma_initial<1><<<grid, 160, smem, s>>>(p);
+  if (kind == 0) k_umma_initial<0><<<grid, 160, smem, s>>>(p);
+  else if (kind == 1) k_umma_initial<1><<<grid, 160, smem, s>>>(p);
   else k_umma_initial<2><<<grid, 160, smem, s>>>(p);
   return cudaGetLastError();
 }
