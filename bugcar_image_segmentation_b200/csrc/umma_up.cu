@@ -45,8 +45,12 @@ struct UpSmem {
   static constexpr int WT_BYTES = 4 * CI * RB;
   static constexpr int W3_BYTES = COUT * RB;
   static constexpr int W1N_BYTES = 16 * 128;           // next projection [16][64] (COUT == 64 only)
-  static constexpr int OFF_X = 0;                      // 2 buffers
-  static constexpr int OFF_E1 = OFF_X + 2 * XBUF;
+  // upsample5_0 (COUT = 16) is small enough for three CTAs per SM with one x buffer and D_c aliased
+  // onto D_b (dead once epilogue B has read it); upsample4_0 fills the SM with one CTA
+  static constexpr int MINB = COUT == 16 ? 3 : 1;
+  static constexpr int NXB = COUT == 16 ? 1 : 2;       // x buffers
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_E1 = OFF_X + NXB * XBUF;
   static constexpr int OFF_E2 = OFF_E1 + ((E_TILE + 1023) / 1024) * 1024;
   static constexpr int OFF_OUT = OFF_E2 + 4 * E_TILE;
   static constexpr int OFF_W = OFF_OUT + OUT_BYTES;
@@ -59,12 +63,14 @@ struct UpSmem {
   static constexpr int NF = 3 * COUT + 4 * CI + 32;
   static constexpr int OFF_BAR = OFF_F + ((NF * 4 + 63) / 64) * 64;
   static constexpr int TOTAL = OFF_BAR + 192;
-  static constexpr uint32_t COL_A = 0, COL_B = N1, COL_C = N1 + 4 * CI, COL_D = COL_B;
-  static constexpr uint32_t TMEM_COLS = (N1 + 4 * CI + 4 * COUT) <= 256 ? 256 : 512;
+  static constexpr uint32_t COL_A = 0, COL_B = N1, COL_C = COUT == 16 ? COL_B : N1 + 4 * CI, COL_D = COL_B;
+  static constexpr uint32_t COLS_USED = COL_C + 4 * COUT;
+  static constexpr uint32_t TMEM_COLS = COLS_USED <= 128 ? 128 : COLS_USED <= 256 ? 256 : 512;
+  static_assert(COUT != 16 || 4 * COUT <= 4 * CI, "D_c must fit over D_b");
 };
 
 template <int CIN, int CI, int COUT>
-__global__ void __launch_bounds__(192, (COUT == 16 ? 2 : 1))
+__global__ void __launch_bounds__(192, (UpSmem<CIN, CI, COUT>::MINB))
 k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box [128][64], 128-byte swizzle
           const __grid_constant__ CUtensorMap map_y,   // 2D [high px][COUT], box = one staged row
           const __grid_constant__ UpParams p) {
@@ -107,8 +113,8 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
   if (warp == 0) {
     for (int k = 0; k < T; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
-      const int b = k & 1;
-      if (k >= 2) mbar_wait(bar(X_EMPTY0 + b), ((k >> 1) - 1) & 1);
+      const int b = k % S::NXB;
+      if (k >= S::NXB) mbar_wait(bar(X_EMPTY0 + b), ((k / S::NXB) - 1) & 1);
       mbar_expect_tx_e(bar(X_FULL0 + b), S::XBUF);
       for (int s = 0; s < S::NSUB; ++s)
         tma_load_2d_e(sbase + S::OFF_X + b * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(X_FULL0 + b));
@@ -116,9 +122,9 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
   } else if (warp == 1) {
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
-      const int b = k & 1;
+      const int b = k % S::NXB;
       // G1: [main | e1] = x * B1^T
-      mbar_wait(bar(X_FULL0 + b), (k >> 1) & 1);
+      mbar_wait(bar(X_FULL0 + b), (k / S::NXB) & 1);
       if (k >= 1) mbar_wait(bar(OUT_FULL), (k - 1) & 1);       // epilogue done reading main of tile k-1
       tc_fence_after();
 #pragma unroll
@@ -367,8 +373,8 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  static_assert(COUT != 16 || ((S::TOTAL + 2048) * 2 <= 233472 && S::TMEM_COLS * 2 <= 512), "two CTAs per SM");
-  const int ctas = num_sms * (COUT == 16 ? 2 : 1);       // upsample5_0 fits twice per SM: two tiles in flight
+  static_assert((S::TOTAL + 2048) * S::MINB <= 233472 && S::TMEM_COLS * S::MINB <= 512, "CTAs per SM");
+  const int ctas = num_sms * S::MINB;                    // upsample5_0 fits three times per SM: three tiles in flight
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   k_umma_up<CIN, CI, COUT><<<grid, 192, smem, s>>>(mx, my, p);
   return cudaGetLastError();

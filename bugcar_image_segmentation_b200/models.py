@@ -67,7 +67,7 @@ class ENET(InferenceModel):
                               "(the reference's trained blobs are not part of its source tree)")
                 GRAPH_PB_PATH = runtime.SYNTHETIC_WEIGHTS
         if str(GRAPH_PB_PATH).endswith((".pb", ".h5")):
-            raise ValueError("TensorFlow/Keras blobs are not read directly: convert with tools/convert_h5.py "
+            raise ValueError("TensorFlow/Keras blobs are not read directly: convert with tools/convert_weights.py "
                              "to a .bcw container first")
         with open(GRAPH_PB_PATH, "rb") as f:     # models.py:25-26
             blob = f.read()

@@ -137,3 +137,17 @@ dist.destroy_process_group()
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "gather ok" in r.stdout
+
+
+def test_state_dict_converter_roundtrip(tmp_path, synthetic_weights):
+    """tools/convert_weights.py: a PyTorch state_dict of the canonical ENet -> the same container"""
+    import torch
+    blob, w, nc, eps = synthetic_weights
+    sd = {("module." + k): torch.from_numpy(v) for k, v in w.items()}
+    sd["module.initial_block.batch_norm.num_batches_tracked"] = torch.tensor(3)
+    src, dst = tmp_path / "enet.pth", tmp_path / "enet.bcw"
+    torch.save({"state_dict": sd, "epoch": 1}, src)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_weights.py"), str(src), str(dst),
+                        "--classes", str(nc)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert dst.read_bytes() == blob
