@@ -38,9 +38,8 @@ struct UmmaParams {
   int rows_per_tile;    // image rows a tile spans (128 / W)
   int ntaps;
   int8_t dy[9], dx[9];
-  int conv_only;        // 1: write epilogue-1 output to `out_small` and stop (first half of asymmetric)
   int has_next;         // 1: compute the next block's projection from the y tile
-  bf16* out_small;      // e2 (conv_only) or e1' (has_next): [pixels][CI]
+  bf16* out_small;      // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
   const uint8_t* wblob; // packed weights, exact shared-memory image (see UmmaSmem)
   // fp32 bias / PReLU-slope block b2[CI] a2[CI] b3[C] a3[C] aout[C] b1n[CN] a1n[CN], by value: the
   // epilogues index it with compile-time channel numbers, so every use is a constant-bank operand
@@ -65,7 +64,9 @@ struct UmmaWeights {
 
 // CN = width of the next block's projection, CRES = residual channels (C: regular bottleneck,
 // < C: down-sampling bottleneck), NG = epilogue groups per CTA (tiles in flight), MINB = CTAs per SM
-template <int C, int CI, int CN, int CRES, int NG_, int MINB_>
+// CONV: conv-only specialisation (first half of an asymmetric bottleneck: taps -> e2 in global memory);
+// no residual / y tiles, no e2 tile, only the conv weights: small enough for two CTAs per SM
+template <int C, int CI, int CN, int CRES, int NG_, int MINB_, bool CONV = false>
 struct UmmaSmem {
   using Wt = UmmaWeights<C, CI, CN>;
   static constexpr int NG = NG_, MINB = MINB_;
@@ -77,18 +78,19 @@ struct UmmaSmem {
   static constexpr int NSUB = C / 64;
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
   static constexpr int NX = NG + 1;                 // residual tile ring (one tile of prefetch)
-  static constexpr int NY = NARROW ? NG : NX;       // C-wide tiles: x/y in place, or one y per group
+  static constexpr int NY = CONV ? 0 : NARROW ? NG : NX;   // C-wide tiles: x/y in place, or one y per group
   static constexpr int RES_RB = CRES * 2 >= 128 ? 128 : CRES * 2;   // row bytes / swizzle of a narrow residual tile
-  static constexpr int RBUF = NARROW ? 128 * CRES * 2 : 0;
+  static constexpr int RBUF = (NARROW && !CONV) ? 128 * CRES * 2 : 0;
   static constexpr int NRING = (MINB == 1 && CI == 16) ? 18 : 9;   // conv-tap ring slots
   // offsets (all multiples of 1024)
   static constexpr int OFF_X = 0;
   static constexpr int OFF_R = OFF_X + NY * XBUF;
   static constexpr int OFF_TAPS = OFF_R + NX * RBUF;
   static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;         // one e2 tile per group
-  static constexpr int OFF_W = OFF_E2 + NG * TAP_BYTES;               // weight image starts here
+  static constexpr int OFF_W = OFF_E2 + (CONV ? 0 : NG) * TAP_BYTES;  // weight image starts here
   static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
-  static constexpr int OFF_BAR = OFF_W + ((Wt::W_BYTES + 1023) / 1024) * 1024;
+  static constexpr int W_LOAD = CONV ? 9 * Wt::W2_TAP : Wt::W_BYTES;  // bytes of the weight image this kernel needs
+  static constexpr int OFF_BAR = OFF_W + ((W_LOAD + 1023) / 1024) * 1024;
   static constexpr int TOTAL = OFF_BAR + 1024;
   // barriers
   static constexpr int X_FULL = 0, D1_FULL = X_FULL + NX, D1_EMPTY = D1_FULL + NG,
@@ -100,7 +102,7 @@ struct UmmaSmem {
   static_assert(TOTAL + 1024 <= 232448 && (TOTAL + 2048) * MINB <= 233472, "shared memory budget");
   // TMEM columns: every group owns a D1 / D2 / D3 accumulator
   static constexpr uint32_t COL_D1 = 0, COL_D2 = NG * CI, COL_D3 = NG * (CI + C);
-  static constexpr uint32_t COLS_USED = NG * (CI + C + CN);
+  static constexpr uint32_t COLS_USED = CONV ? NG * CI : NG * (CI + C + CN);
   static constexpr uint32_t TMEM_COLS = COLS_USED <= 32 ? 32 : COLS_USED <= 64 ? 64 : COLS_USED <= 128 ? 128
                                         : COLS_USED <= 256 ? 256 : 512;
   static_assert(COLS_USED <= 512 && TMEM_COLS * MINB <= 512, "TMEM budget");
@@ -119,14 +121,14 @@ struct UmmaSmem {
 //   warps 4.. epilogue       group g = (warp - 4) / 4; one TMEM lane (= pixel) per thread:
 //                            D1 -> e2 (smem), D2 + x -> y (smem, TMA store), D3 -> e1' (global);
 //                            its first thread stores y and requests the x tile that reuses the buffer
-template <int C, int CI, int CN, int CRES, int NG, int MINB>
+template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
 __global__ void __launch_bounds__(128 + 128 * NG, MINB)
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                                                                 // (narrow: [pixels][CRES], box [128 px][CRES])
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
                   const __grid_constant__ UmmaParams p) {
-  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
   using Wt = UmmaWeights<C, CI, CN>;
   constexpr int RB = S::RB;
   constexpr int NX = S::NX;
@@ -151,8 +153,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       mbar_init(bar(i), by_group ? 128 : 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar(S::W_FULL), Wt::W_BYTES);
-    bulk_load(sbase + S::OFF_W, p.wblob, Wt::W_BYTES, bar(S::W_FULL));
+    mbar_expect_tx(bar(S::W_FULL), S::W_LOAD);
+    bulk_load(sbase + S::OFF_W, p.wblob, S::W_LOAD, bar(S::W_FULL));
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
@@ -164,7 +166,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t IDESC_CONV = instr_desc(128, CI), IDESC_EXP = instr_desc(128, C), IDESC_PROJ = instr_desc(128, CN);
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // my tiles
-  const bool full = !p.conv_only;
+  constexpr bool full = !CONV;
 
   // Service warps run their loops convergently (all 32 lanes) and elect one lane per instruction
   // inside the asm (umma_common.cuh): no divergence, no per-lane operand recomputation.
@@ -273,7 +275,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         mbar_arrive(bar(S::D1_EMPTY + grp));
 #pragma unroll
         for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + p.f[F_B2 + j], p.f[F_A2 + j]);
-        if (!full) {
+        if constexpr (!full) {
           uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
 #pragma unroll
           for (int c = 0; c < CI / 8; ++c)
@@ -528,10 +530,10 @@ void umma_free(UmmaPack& p) {
   p = UmmaPack();
 }
 
-template <int C, int CI, int CN, int CRES, int NG, int MINB>
+template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
 static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
-  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
   CUtensorMap me1, mx, my;
   if (!make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
@@ -549,7 +551,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   p.rows_per_tile = 128 / W > 0 ? 128 / W : 1;
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) { p.dy[t] = taps.dy[t]; p.dx[t] = taps.dx[t]; }
-  p.conv_only = conv_only;
+  if ((conv_only != 0) != CONV) return cudaErrorInvalidValue;
   p.has_next = has_next;
   p.out_small = out_small;
   p.wblob = pk.wblob;
@@ -557,14 +559,14 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   static bool attr_done = false;
   const int smem = S::TOTAL + 1024;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI, CN, CRES, NG, MINB>,
+    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const int ctas = num_sms * MINB;
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
+  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }
 
@@ -581,7 +583,11 @@ cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16*
   static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 22);
 #define BC_LAUNCH(C_, CI_, CN_, CR_, NG_, MB_) \
   return launch_one<C_, CI_, CN_, CR_, NG_, MB_>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s)
-  if (pk.C == 128 && pk.CI == 32 && pk.CRES == 128) BC_LAUNCH(128, 32, 32, 128, 2, 1);
+  if (pk.C == 128 && pk.CI == 32 && pk.CRES == 128) {
+    if (conv_only)
+      return launch_one<128, 32, 32, 128, 2, 2, true>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, 1, 0, num_sms, s);
+    BC_LAUNCH(128, 32, 32, 128, 2, 1);
+  }
   if (pk.C == 64 && pk.CI == 16 && pk.CRES == 64) {
     if (cfg64 == 12) BC_LAUNCH(64, 16, 16, 64, 1, 2);
     if (cfg64 == 41) BC_LAUNCH(64, 16, 16, 64, 4, 1);
