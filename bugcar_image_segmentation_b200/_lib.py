@@ -37,6 +37,8 @@ SIGNATURES = {
     "bc_enet_block_output": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "bc_enet_labels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bc_argmax_lut": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "bc_contour_noise_removal": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "bc_set_contour_filter": (_i, [_vp, _i]),
     "bc_occgrid_shape": (_i, [_vp, _d, _d, _d, C.POINTER(_i), C.POINTER(_i)]),
     "bc_occgrid": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp]),
     "bc_pipeline": (_i, [_vp, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _i, _vp, _vp, _vp]),
@@ -173,6 +175,13 @@ class Context:
     def argmax_lut(self, d_logits, B, Cn, H, W, lut, d_labels, stream=None):
         self._ck(self.lib.bc_argmax_lut(self.h, _ptr(d_logits), B, Cn, H, W, _lut(lut), _ptr(d_labels),
                                         _ptr(stream)))
+
+    def contour_noise_removal(self, d_seg, H, W, B, d_out, stream=None):
+        self._ck(self.lib.bc_contour_noise_removal(self.h, _ptr(d_seg), int(H), int(W), int(B), _ptr(d_out),
+                                                   _ptr(stream)))
+
+    def set_contour_filter(self, on):
+        self._ck(self.lib.bc_set_contour_filter(self.h, int(bool(on))))
 
     def occgrid_shape(self, w_m, h_m, cell_m):
         hc, wc = _i(), _i()

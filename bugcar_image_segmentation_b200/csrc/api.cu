@@ -133,6 +133,12 @@ struct bc_ctx {
   // ---- K9 coordinate tables, keyed by the geometry (cleared by bc_set_bev)
   std::vector<std::pair<BevGeom, uint4*>> occ_tables;
 
+  // ---- contour_noise_removal (image_processing_utils.py:4-44)
+  void* cn_scratch = nullptr;
+  size_t cn_scratch_bytes = 0;
+  uint8_t* d_labels_cn = nullptr;     // filtered road masks of the binary pipeline [max_batch][256][512]
+  int contour_filter = 0;
+
   // ---- multi-GPU gather
   int8_t* gather_base = nullptr;
   int rank = 0, world = 1;
@@ -906,6 +912,25 @@ int8_t* grid_dest(bc_ctx* c, int8_t* d_grids, int B, const BevGeom& g) {
   return c->gather_base + (size_t)c->rank * B * g.Hc * g.Wc;
 }
 
+int ensure_contour_scratch(bc_ctx* c, int B, int H, int W) {
+  size_t need = contour_scratch_bytes(B, H, W);
+  if (need <= c->cn_scratch_bytes) return BC_OK;
+  if (c->cn_scratch) { cudaFree(c->cn_scratch); c->cn_scratch = nullptr; c->cn_scratch_bytes = 0; }
+  if (cudaMalloc(&c->cn_scratch, need) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, BC_ERR_NOMEM, "contour_noise_removal scratch: out of device memory");
+  }
+  c->cn_scratch_bytes = need;
+  return BC_OK;
+}
+
+// 8 kernels (contour.cu); algorithmic traffic = mask in + mask out
+void run_contour(bc_ctx* c, const uint8_t* seg, int H, int W, int B, uint8_t* out, cudaStream_t s) {
+  L(c, "contour_noise_removal", 2.0 * B * H * W, 0, s,
+    [&] { launch_contour_noise_removal(seg, H, W, B, out, c->cn_scratch, s); });
+  c->launches += contour_launch_count() - 1;
+}
+
 Lut256 make_lut(const uint8_t* h_lut) {
   Lut256 l;
   memcpy(l.v, h_lut, 256);
@@ -925,6 +950,10 @@ int do_pipeline(bc_ctx* c, const uint8_t* d_bgr, int h, int w, int B, const uint
   uint8_t* labels = d_labels_out ? d_labels_out : c->d_labels;
   Lut256 lut = make_lut(h_lut);
   if ((r = forward(c, frames, BC_IN_BGR_U8, B, nullptr, labels, &lut, s))) return r;
+  if (g.binary && c->contour_filter) {           // predict_binary -> contour_noise_removal -> grid
+    run_contour(c, labels, BC_NET_H, BC_NET_W, B, c->d_labels_cn, s);
+    labels = c->d_labels_cn;
+  }
   L(c, "occgrid", (double)B * ((double)g.in_rows * g.in_cols + (double)g.Hc * g.Wc), 0, s,
     [&] { launch_occgrid(labels, B, g, d_grids, s); });
   return check_launch(c, "pipeline");
@@ -946,6 +975,7 @@ int run_pipeline(bc_ctx* c, const uint8_t* d_bgr, int h, int w, int B, const uin
   memset(&key, 0, sizeof key);
   key.in = d_bgr; key.out = d_grids; key.labels = d_labels_out;
   key.h = h; key.w = w; key.B = B; key.binary = g.binary; key.ros = g.ros_layout;
+  key.pad_ = c->contour_filter;
   key.w_m = w_m; key.h_m = h_m; key.cell_m = cell_m;
   memcpy(key.lut, h_lut, 256);
   GraphEntry* ge = nullptr;
@@ -1048,7 +1078,8 @@ void bc_destroy(bc_ctx* c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto e : c->copy_done) if (e) cudaEventDestroy(e);
   if (c->call_start) cudaEventDestroy(c->call_start);
-  void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out};
+  void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out, c->cn_scratch,
+                c->d_labels_cn};
   for (void* p : ps) if (p) cudaFree(p);
   delete c;
 }
@@ -1204,6 +1235,35 @@ int bc_argmax_lut(bc_ctx* c, const float* d_logits, int B, int C, int H, int W, 
   L(c, "argmax_lut", (double)B * H * W * (4.0 * C + 1), 0, (cudaStream_t)stream,
     [&] { launch_argmax_lut(d_logits, B, C, H, W, make_lut(h_lut), d_labels, (cudaStream_t)stream); });
   return check_launch(c, "argmax_lut");
+}
+
+int bc_contour_noise_removal(bc_ctx* c, const uint8_t* d_seg, int H, int W, int B, uint8_t* d_out, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_seg || !d_out) return fail(c, BC_ERR_ARG, "null pointer");
+  if (std::min(H, W) < 50) return fail(c, BC_ERR_ARG, "contour_noise_removal needs min(h, w) >= 50 (closing kernel int(min/50))");
+  if (std::min(H, W) >= 1650) return fail(c, BC_ERR_ARG, "contour_noise_removal supports closing kernels up to 32 x 32 (min(h, w) < 1650)");
+  if (B < 1 || (long long)B * H * W > 0x7fffffffLL) return fail(c, BC_ERR_ARG, "bad batch size");
+  CU(cudaSetDevice(c->device));
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (stream) cudaStreamIsCapturing((cudaStream_t)stream, &st);
+  if (st != cudaStreamCaptureStatusNone && contour_scratch_bytes(B, H, W) > c->cn_scratch_bytes)
+    return fail(c, BC_ERR_STATE, "contour_noise_removal scratch must be sized by one call outside stream capture");
+  int r = ensure_contour_scratch(c, B, H, W);
+  if (r) return r;
+  run_contour(c, d_seg, H, W, B, d_out, (cudaStream_t)stream);
+  return check_launch(c, "contour_noise_removal");
+}
+
+int bc_set_contour_filter(bc_ctx* c, int enable) {
+  if (!c) return BC_ERR_ARG;
+  if (enable) {      // size everything for max_batch now: the pipeline may run inside a graph capture later
+    CU(cudaSetDevice(c->device));
+    int r = ensure_contour_scratch(c, c->max_batch, BC_NET_H, BC_NET_W);
+    if (r) return r;
+    if (!c->d_labels_cn) CU(cudaMalloc(&c->d_labels_cn, (size_t)c->max_batch * BC_NET_H * BC_NET_W));
+  }
+  c->contour_filter = enable ? 1 : 0;
+  return BC_OK;
 }
 
 int bc_occgrid_shape(bc_ctx* c, double w_m, double h_m, double cell_m, int* Hc, int* Wc) {

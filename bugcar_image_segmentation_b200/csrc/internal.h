@@ -149,4 +149,12 @@ void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lu
 void launch_occ_table(const BevGeom& g, uint4* table, cudaStream_t s);     // [25][Hc*Wc] entries, once per geometry
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s);   // needs g.table
 
+
+// ------------------------------------------------------------------ launchers (contour.cu)
+// contour_noise_removal (image_processing_utils.py:4-44): uint8 masks (B,H,W) -> uint8 0/1 masks.
+// `scratch` must hold contour_scratch_bytes(B,H,W) bytes; needs 50 <= min(H,W) < 1650.
+size_t contour_scratch_bytes(int B, int H, int W);
+int contour_launch_count();
+void launch_contour_noise_removal(const uint8_t* seg, int H, int W, int B, uint8_t* out, void* scratch, cudaStream_t s);
+
 }  // namespace bc

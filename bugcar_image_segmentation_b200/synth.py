@@ -98,3 +98,56 @@ def region_frame(seed, h=INPUT_H, w=INPUT_W, n_rect=24):
         gain[y0:y0 + rh, x0:x0 + rw] = rng.uniform(0.88, 1.12)
     img = PALETTE[lab].astype(np.float64) * gain[:, :, None] + rng.normal(0.0, 8.0, (h, w, 3))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8), lab
+
+
+def road_mask(seed, h=INPUT_H, w=INPUT_W):
+    """Binary road mask (uint8 0/1, or 0/arbitrary non-zero for seed % 7 == 6) as predict_binary
+    would deliver it, for contour_noise_removal parity: seed % 7 picks white noise, coarse
+    blocks, nested rings anchored in the bottom strip (kept hole contours, islands in holes),
+    or a road trapezoid with elliptical holes, islands and salt-and-pepper noise."""
+    rng = np.random.default_rng(seed)
+    kind = seed % 7
+    yy, xx = np.mgrid[0:h, 0:w]
+    if kind == 0:
+        return (rng.random((h, w)) < rng.uniform(0.2, 0.8)).astype(np.uint8)
+    if kind == 1:
+        s = int(rng.integers(2, 16))
+        m = (rng.random((h // s + 1, w // s + 1)) < rng.uniform(0.3, 0.8)).astype(np.uint8)
+        return np.ascontiguousarray(np.kron(m, np.ones((s, s), np.uint8))[:h, :w])
+    m = np.zeros((h, w), np.uint8)
+    if kind == 2:
+        x0 = 0 if rng.random() < .5 else int(rng.integers(0, w // 8))
+        x1 = w if rng.random() < .5 else w - int(rng.integers(0, w // 8))
+        y0 = int(rng.integers(0, h // 2))
+        y1 = h if rng.random() < .5 else h - int(rng.integers(0, 4))
+        v = 1
+        for _ in range(int(rng.integers(1, 6))):
+            if x1 - x0 < 4 or y1 - y0 < 4:
+                break
+            if rng.random() < 0.5:
+                m[y0:y1, x0:x1] = v
+            else:
+                cx, cy = (x0 + x1) / 2, (y0 + y1) / 2
+                m[((xx - cx) / ((x1 - x0) / 2)) ** 2 + ((yy - cy) / ((y1 - y0) / 2)) ** 2 <= 1] = v
+            v ^= 1
+            x0 += int(rng.integers(1, max(2, (x1 - x0) // 6)))
+            x1 -= int(rng.integers(1, max(2, (x1 - x0) // 6)))
+            y0 += int(rng.integers(1, max(2, (y1 - y0) // 6)))
+            y1 -= int(rng.integers(1, max(2, (y1 - y0) // 8)))
+        m[rng.random((h, w)) < rng.uniform(0, 0.05)] ^= 1
+        return m
+    top = int(rng.integers(h // 4, 3 * h // 4))
+    m[(yy > top) & (np.abs(xx - w / 2) < (yy - top) * rng.uniform(1, 4) + 20)] = 1
+    for _ in range(int(rng.integers(0, 6))):
+        cx, cy = int(rng.integers(0, w)), int(rng.integers(h // 2, h))
+        rx, ry = int(rng.integers(5, max(6, w // 2))), int(rng.integers(3, max(4, h // 6)))
+        e = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2
+        m[e < 1] = 0
+        if rng.random() < 0.7:
+            m[e < rng.uniform(0.1, 0.7)] = 1
+            if rng.random() < 0.5:
+                m[e < rng.uniform(0.01, 0.1)] = 0
+    m[rng.random((h, w)) < rng.uniform(0, 0.08)] ^= 1
+    if kind == 6:
+        m = m * rng.integers(1, 255, (h, w)).astype(np.uint8)
+    return m

@@ -135,6 +135,20 @@ int bc_occgrid_shape(bc_ctx* ctx, double w_m, double h_m, double cell_m, int* Hc
 int bc_occgrid(bc_ctx* ctx, const uint8_t* d_labels, int B, double w_m, double h_m,
                double cell_m, int binary, int ros_layout, int8_t* d_grids, void* stream);
 
+/* ---- contour_noise_removal  (image_processing_utils.py:4-44) ----------------------------- */
+/* d_seg uint8 (B,H,W) road masks (non-zero = road, as ENET.predict_binary returns them) ->
+ * d_out uint8 (B,H,W) in {0,1}: k x k close with k = int(min(H,W)/50) (:6-9), then every contour
+ * (findContours RETR_LIST, :12) whose fillPoly covers more than 40 % of the bottom tenth of the
+ * image (:19-39) is kept, and all kept contours are filled together, even-odd (:41-42).  Computed
+ * by connected-component labelling, bit-exact with the OpenCV formulation.  Needs
+ * 50 <= min(H,W) < 1650.  Scratch grows on demand (a first call must happen outside graph capture). */
+int bc_contour_noise_removal(bc_ctx* ctx, const uint8_t* d_seg, int H, int W, int B, uint8_t* d_out,
+                             void* stream);
+/* 1: bc_pipeline* calls with binary = 1 run predict_binary -> contour_noise_removal -> grid, the
+ * order the reference intends (models.py:6 imports the filter next to predict_binary);
+ * 0 (default): the mask goes to the grid unfiltered. */
+int bc_set_contour_filter(bc_ctx* ctx, int enable);
+
 /* ---- whole path --------------------------------------------------------------------- */
 /* frames (B,h,w,3) uint8 BGR -> grids: resize (if needed) -> ENet -> argmax+LUT -> grid.
  * d_labels_out may be NULL (labels then live only in context scratch). */

@@ -10,6 +10,7 @@ regenerates them); large outputs are stored as sha256 + a strided sample.
   pre.npz          reference ENET.preprocess on native / 720p / odd-size frames (models.py:84-95)
   resize.npz       cv2.resize(bgr,(512,256)) hashes                     (models.py:87)
   argmax.npz       logits with ties -> labels (np.argmax == tf.math.argmax tie-break; models.py:55-58)
+  contour.npz      reference contour_noise_removal on synth.road_mask seeds (image_processing_utils.py:4-44)
   enet.npz         oracle (torch fp32) logits sample for the synthetic weights: PARITY UNPINNED,
                    guards the oracle against drift only
 """
@@ -104,6 +105,18 @@ def main():
     np.savez_compressed(os.path.join(OUT, "argmax.npz"), seed=77,
                         labels3=pre_oracle.labels_from_logits(logits, pre_oracle.LUT_3WAY),
                         labels2=pre_oracle.labels_from_logits(logits, pre_oracle.LUT_BINARY))
+
+    # ---- contour_noise_removal (8f-2)
+    cn = {"seeds": np.arange(28), "shapes": np.array([[256, 512], [256, 512], [120, 200], [360, 640]])}
+    for s_ in cn["seeds"]:
+        h, w = cn["shapes"][s_ % 4]
+        m = synth.road_mask(int(s_), int(h), int(w))
+        out = ref.image_processing_utils.contour_noise_removal(m)
+        assert out.dtype == np.uint8 and out.shape == m.shape and out.max() <= 1
+        k = int(min(h, w) / 50)
+        cn[f"out_{s_}"] = np.packbits(out)
+        cn[f"closed_sha_{s_}"] = np.array(sha(cv2.morphologyEx(m, cv2.MORPH_CLOSE, np.ones((k, k), np.uint8))))
+    np.savez_compressed(os.path.join(OUT, "contour.npz"), **cn)
 
     # ---- ENet oracle self-pin
     with open(os.path.join(ROOT, "pretrained_models", "enet_synthetic_seed42.bcw"), "rb") as f:
