@@ -1242,7 +1242,8 @@ int bc_contour_noise_removal(bc_ctx* c, const uint8_t* d_seg, int H, int W, int 
   if (!d_seg || !d_out) return fail(c, BC_ERR_ARG, "null pointer");
   if (std::min(H, W) < 50) return fail(c, BC_ERR_ARG, "contour_noise_removal needs min(h, w) >= 50 (closing kernel int(min/50))");
   if (std::min(H, W) >= 1650) return fail(c, BC_ERR_ARG, "contour_noise_removal supports closing kernels up to 32 x 32 (min(h, w) < 1650)");
-  if (B < 1 || (long long)B * H * W > 0x7fffffffLL) return fail(c, BC_ERR_ARG, "bad batch size");
+  if (B < 1 || B > 65535 || H > 65535 || (long long)B * H * W > 0x7fffffffLL)
+    return fail(c, BC_ERR_ARG, "batch size outside [1, 65535] or more than 2^31 pixels");
   CU(cudaSetDevice(c->device));
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (stream) cudaStreamIsCapturing((cudaStream_t)stream, &st);
