@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
+    ap.add_argument("--skip-contour", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true")
     ap.add_argument("--weights", default=WEIGHTS, choices=sorted(WEIGHT_FILES))
     ap.add_argument("--frames", default=FRAMES, choices=["scene", "noise"])
@@ -382,6 +383,38 @@ def main():
                    "mean_ms": float(ts.mean()), "frames": int(ts.size),
                    "how": "bc_pipeline_host, bs 1, pinned host frame -> grid on host, wall clock"}
 
+    # ---- predict_binary -> contour_noise_removal -> grid (binary pipeline with the filter on)
+    contour = None
+    if rank == 0 and world == 1 and not args.skip_contour:
+        from oracle import contour_oracle
+        lut2 = np.zeros(256, np.uint8)
+        lut2[[0, 1]] = 1                                   # models.py:79-80
+        d_lab = torch.empty((B, 256, 512), dtype=torch.uint8, device="cuda")
+        d_filt = torch.empty_like(d_lab)
+        res = {}
+        for on in (0, 1):
+            model.ctx.set_contour_filter(on)
+            run = lambda i: model.ctx.pipeline(dev_sets[i % N_INPUT_SETS], 256, 512, B, lut2, *GRID, 1, 0, d_lab, d_grids,
+                                               stream.cuda_stream)
+            for i in range(3):
+                run(i)
+            res[on] = B * 10 / (timed(run, 10) / 1e3)
+        model.ctx.set_contour_filter(0)
+        run_f = lambda i: model.ctx.contour_noise_removal(d_lab, 256, 512, B, d_filt, stream.cuda_stream)
+        for i in range(3):
+            run_f(i)
+        ms_f = timed(run_f, 10) / 10
+        masks = d_lab[:8].cpu().numpy()
+        t0 = time.perf_counter()
+        want = [contour_oracle.contour_noise_removal_cv2(m) for m in masks]
+        cpu_ms = (time.perf_counter() - t0) / len(masks) * 1e3
+        exact = bool(np.array_equal(np.stack(want), d_filt[:8].cpu().numpy()))
+        contour = {"binary_pipeline_frames_per_s": res[0], "binary_pipeline_with_filter_frames_per_s": res[1],
+                   "filter_alone_ms_per_batch": ms_f, "filter_alone_frames_per_s": B / ms_f * 1e3,
+                   "filter_algorithmic_gbs": 2 * B * 131072 / (ms_f * 1e-3) / 1e9,
+                   "cpu_opencv_ms_per_frame": cpu_ms, "bit_exact_vs_opencv_on_8_frames": exact,
+                   "masks": "predict_binary labels of the benchmark batch"}
+
     # ---- CPU baseline on a bounded sample (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -417,7 +450,7 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "latency_bs1": latency, "kernels": kernels,
+            "latency_bs1": latency, "contour_filter": contour, "kernels": kernels,
         }))
     if world > 1:
         dist.destroy_process_group()

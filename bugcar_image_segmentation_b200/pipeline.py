@@ -10,6 +10,9 @@ GPU through ``bc_pipeline`` / ``bc_pipeline_host`` (one CUDA graph per argument 
 is the fused equivalent of
     seg = model.predict(np.concatenate([ENET.preprocess(f) for f in frames]))
     grids = [bev.create_occupancy_grid(s, 10.0, 10.0, 0.1) for s in seg]
+and, with ``binary=True, contour_filter=True``, of
+    seg = model.predict_binary(...)
+    grids = [bev.create_occupancy_grid_binary(contour_noise_removal(s), 10.0, 10.0, 0.1) for s in seg]
 """
 import numpy as np
 
@@ -18,7 +21,7 @@ from . import runtime
 
 class FramePipeline:
     def __init__(self, model, bev, grid_width_in_m, grid_height_in_m, cell_size_in_m, binary=False,
-                 ros_layout=False):
+                 ros_layout=False, contour_filter=False):
         if bev.laserscan_like_occupancy_grid:
             raise NotImplementedError("laserscan-like grids are not reproduced (bev.py:216-240)")
         self.model, self.bev = model, bev
@@ -26,6 +29,10 @@ class FramePipeline:
         self.w_m, self.h_m, self.cell_m = float(grid_width_in_m), float(grid_height_in_m), float(cell_size_in_m)
         self.binary, self.ros_layout = int(bool(binary)), int(bool(ros_layout))
         self.lut = model.LUT_BINARY if binary else model.LUT_3WAY
+        if contour_filter and not binary:
+            raise ValueError("contour_noise_removal works on the binary road mask (image_processing_utils.py:4): "
+                             "use binary=True")
+        self.ctx.set_contour_filter(bool(contour_filter))      # a property of the context's binary pipeline
         self.Hc, self.Wc = self.ctx.occgrid_shape(self.w_m, self.h_m, self.cell_m)
         self._torch, self.device = model._torch, model.device
         self._pinned_in = None

@@ -146,3 +146,30 @@ def contour_noise_removal(segmap: np.ndarray) -> np.ndarray:
     val = np.where(on_kept_ring, 1, val)
     out[corefg] = val[corefg]
     return out
+
+
+def contour_noise_removal_cv2(segmap: np.ndarray) -> np.ndarray:
+    """The same function through the OpenCV calls the reference makes
+    (image_processing_utils.py:9 morphologyEx, :12 findContours(mode 1 = RETR_LIST, method 2 =
+    CHAIN_APPROX_SIMPLE), :35/:42 fillPoly): the CPU baseline bench.py times, and a second,
+    contour-based opinion for the connected-component restatement above."""
+    import cv2
+    seg = np.ascontiguousarray(segmap, dtype=np.uint8)
+    h, w = seg.shape
+    k = int(min(h, w) / 50)
+    closed = cv2.morphologyEx(seg, cv2.MORPH_CLOSE, np.ones((k, k), np.uint8))
+    contours, _ = cv2.findContours(closed, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    y_top = int(h * (1 - LENGTH_RATIO))
+    limit = w * (h - y_top) * MASK_AREA_THRESH
+    kept = []
+    for c in contours:
+        if c.shape[0] <= 2:
+            continue
+        filled = np.zeros_like(seg)
+        cv2.fillPoly(filled, [c], 1)
+        if np.count_nonzero(filled[y_top:h]) > limit:
+            kept.append(c)
+    out = np.zeros((h, w), np.uint8)
+    if kept:
+        cv2.fillPoly(out, kept, 1)
+    return out
