@@ -217,6 +217,11 @@ __device__ __forceinline__ bool is_occ(int v, int binary) {
 static constexpr int OCC_FRAMES = 8;
 static constexpr unsigned OCC_INNER = (7u << 6) | (7u << 11) | (7u << 16);     // 3x3 block around bit 12
 
+// outer ring of the 5x5 block, k = 0..15 -> bit position
+__device__ __forceinline__ int occ_outer_pos(int k) {
+  return k < 5 ? k : (k < 11 ? 5 * (((k - 5) >> 1) + 1) + ((k - 5) & 1) * 4 : k + 9);
+}
+
 __global__ void __launch_bounds__(128)
 k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __restrict__ grids) {
   extern __shared__ uint4 tab[];                  // [25][128]
@@ -224,6 +229,8 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
   const int cells = g.Hc * g.Wc;
   const int cell = blockIdx.x * 128 + threadIdx.x;
   const bool live = cell < cells;
+  const int lane = threadIdx.x & 31, half = lane >> 4, k16 = lane & 15;
+  const unsigned half_mask = half ? 0xffff0000u : 0x0000ffffu;
   unsigned inside = 0;
 #pragma unroll
   for (int pos = 0; pos < 25; ++pos) {
@@ -231,47 +238,61 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
     tab[pos * 128 + threadIdx.x] = e;
     if (e.w & 4u) inside |= 1u << pos;
   }
-  if (!live) return;               // each thread reads back only its own column: no barrier needed
+  __syncwarp();                    // a warp reads back only its own 32 columns: no block barrier needed
   const int cx = cell % g.Wc, cy = cell / g.Wc;
   const size_t o = g.ros_layout ? (size_t)(g.Wc - 1 - cx) * g.Hc + (g.Hc - 1 - cy)   // occgrid_to_ros.py:18-21
                                 : (size_t)cell;
   const int rows = g.in_rows, cols = g.in_cols;
   const int n1 = min(B, (int)(blockIdx.y + 1) * OCC_FRAMES);
+  // what this lane does when it helps with another lane's outer ring / opening test
+  const int my_outer = occ_outer_pos(k16);
+  unsigned my_q = 0, my_nb = 0;                    // lanes 0..8 of each half: one erosion centre q each
+  if (k16 < 9) {
+    const int qj = 1 + k16 / 3, qi = 1 + k16 % 3;
+    my_q = 1u << (qj * 5 + qi);
+    for (int rj = -1; rj <= 1; ++rj)
+      for (int ri = -1; ri <= 1; ++ri) my_nb |= 1u << ((qj + rj) * 5 + (qi + ri));
+  }
   for (int n = blockIdx.y * OCC_FRAMES; n < n1; ++n) {
     const uint8_t* lab = labels + (size_t)n * rows * cols;
     int v = occ_sample(lab, tab[12 * 128 + threadIdx.x], cols);
-    if (is_occ(v, g.binary)) {
-      // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i)
-      unsigned occ = 1u << 12;
+    const bool occupied = live && is_occ(v, g.binary);
+    unsigned occ = 1u << 12;       // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i)
+    bool opened = true;
+    if (occupied) {
 #pragma unroll
       for (int pos = 6; pos <= 18; ++pos) {
         if (!((OCC_INNER >> pos) & 1u) || pos == 12) continue;
         if ((inside >> pos) & 1u)
           if (is_occ(occ_sample(lab, tab[pos * 128 + threadIdx.x], cols), g.binary)) occ |= 1u << pos;
       }
-      bool opened = ((~occ) & inside & OCC_INNER) == 0;         // q = p: every in-template neighbour occupied
-      if (!opened) {
-        for (int pos = 0; pos < 25; ++pos) {
-          if (((OCC_INNER >> pos) & 1u) || !((inside >> pos) & 1u)) continue;
-          if (is_occ(occ_sample(lab, tab[pos * 128 + threadIdx.x], cols), g.binary)) occ |= 1u << pos;
-        }
-#pragma unroll
-        for (int qj = 1; qj <= 3; ++qj)
-#pragma unroll
-          for (int qi = 1; qi <= 3; ++qi) {
-            unsigned qbit = 1u << (qj * 5 + qi);
-            if (!(inside & qbit)) continue;            // dilate: outside contributes 0
-            unsigned nb = 0;
-#pragma unroll
-            for (int rj = -1; rj <= 1; ++rj)
-#pragma unroll
-              for (int ri = -1; ri <= 1; ++ri) nb |= 1u << ((qj + rj) * 5 + (qi + ri));
-            // erode: every in-template neighbour must be occupied
-            if (((~occ) & inside & nb) == 0) opened = true;
-          }
-      }
-      if (!opened) v = 2;                             // bev.py:203-205
+      opened = ((~occ) & inside & OCC_INNER) == 0;            // q = p: every in-template neighbour occupied
     }
+    // The undecided cells (occupied, but not the centre of a full 3x3 block) need the outer ring.
+    // They are few, so the warp serves them two at a time: 16 lanes sample one outer pixel each,
+    // 9 lanes test one erosion centre each.
+    unsigned todo = __ballot_sync(0xffffffffu, occupied && !opened);
+    while (todo) {
+      const int s0 = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int s1 = todo ? __ffs(todo) - 1 : -1;
+      if (s1 >= 0) todo &= todo - 1;
+      const int src = half ? s1 : s0;
+      const bool helping = src >= 0;
+      const int srcl = helping ? src : s0;
+      const unsigned s_inside = __shfl_sync(0xffffffffu, inside, srcl);
+      const unsigned s_occ = __shfl_sync(0xffffffffu, occ, srcl);
+      unsigned bit = 0;
+      if (helping && ((s_inside >> my_outer) & 1u))
+        if (is_occ(occ_sample(lab, tab[my_outer * 128 + (threadIdx.x & ~31) + srcl], cols), g.binary)) bit = 1u << my_outer;
+      const unsigned all = s_occ | __reduce_or_sync(half_mask, bit);
+      // opened(p) = OR_q AND_{r in N3(q)} occ(r): dilate ignores q outside the template, erode ignores r outside
+      const bool ok = helping && my_q && (s_inside & my_q) && (((~all) & s_inside & my_nb) == 0);
+      const unsigned okb = __ballot_sync(0xffffffffu, ok);     // the owner may sit in the other half-warp
+      if (lane == s0) opened = (okb & 0xffffu) != 0;
+      if (lane == s1) opened = (okb >> 16) != 0;
+    }
+    if (occupied && !opened) v = 2;                   // bev.py:203-205
     int out;
     if (g.binary) {
       int m = (v * 100) & 255;                        // uint8 * 100 (bev.py:139-142)
@@ -280,7 +301,7 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
       if (v == 3) v = 1;                              // bev.py:242
       out = (v == 0) ? 255 : ((200 - ((v * 100) & 255)) & 255);   // bev.py:244-245
     }
-    grids[(size_t)n * cells + o] = (int8_t)out;
+    if (live) grids[(size_t)n * cells + o] = (int8_t)out;
   }
 }
 
