@@ -417,6 +417,17 @@ bool make_map_e1(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI) 
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle_for(CI * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// same tensor view, explicit box [1][box_rows][box_w][CI]
+bool make_map_box(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI, int box_w, int box_rows) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)CI, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)CI * 2, (cuuint64_t)W * CI * 2, (cuuint64_t)H * W * CI * 2};
+  cuuint32_t box[4] = {(cuuint32_t)CI, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle_for(CI * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // 2D map over [pixels][C] bf16; box = [128 px][64 ch], 128-byte swizzle
 bool make_map_x(CUtensorMap* m, const bf16* base, size_t pixels, int C) {
   PFN_encodeTiled enc = encode_fn();

@@ -209,6 +209,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // host: TMA tensor maps (enet_umma.cu)
 bool make_map_e1(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI);   // 4D [N][H][W][CI], box = 128 px
+bool make_map_box(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI, int box_w, int box_rows);
 bool make_map_x(CUtensorMap* m, const bf16* base, size_t pixels, int C);           // 2D [px][C], box [128][64]
 bool make_map_rows(CUtensorMap* m, const bf16* base, size_t pixels, int C, int box_px, int sw);   // 2D [px][C], box [box_px][C]
 // 5D view [N*Ho][2][Wo][2][C] of a [N][2Ho][2Wo][C] tensor (2x2 stride-2 windows), box [rows][1][box_w][1][C]

@@ -5,8 +5,11 @@
 // Each INPUT pixel (i, j) of the 128x256 map produces the 2x2 output quad (2i+qy, 2j+qx) from
 // its four neighbours (i+di, j+dj): as a GEMM, M = 128 input pixels, K = 4 neighbours x 16
 // channels, N = 4 quad positions x 16 classes, with the taps that do not reach a quad position
-// stored as zeros in B.  Every neighbour slab is one TMA box load of the NHWC activation
-// (shifted by (di, dj); out-of-bounds rows / columns zero-filled = the transposed conv's edge).
+// stored as zeros in B.  The tile's two input rows (i, i+1) arrive as two TMA boxes of 129 pixels
+// (out-of-bounds row / column zero-filled = the transposed conv's edge); the dj = 1 neighbours are
+// the same slabs read through a descriptor that starts one pixel (32 bytes) later -- the 32-byte
+// swizzle is a function of the absolute shared-memory address, for TMA and for the MMA alike --
+// so x crosses L2 -> SM twice per tile instead of four times (the kernel was L2-bandwidth bound).
 //
 // Warp roles as in enet_umma.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
 // (one TMEM lane = one input pixel per thread; 64 fp32 logits -> 4 labels).  Taps and the
@@ -25,30 +28,34 @@ struct HeadParams {
   Lut256 lut;
 };
 
-static constexpr int HEAD_TAP = 128 * 32;      // one neighbour slab: 128 px x 16 ch bf16
+static constexpr int HEAD_ROW = 129 * 32;      // one input row segment + its right neighbour column: 129 px x 16 ch bf16
+static constexpr int HEAD_SLAB = 17 * 256;     // slab pitch: HEAD_ROW rounded up to the 32-byte-swizzle repeat (256 B)
 static constexpr int HEAD_WTAP = 64 * 32;      // one tap of B
-static constexpr int HEAD_OFF_TAPS = 0;        // 2 sets x 4 taps
-static constexpr int HEAD_OFF_W = 2 * 4 * HEAD_TAP;
+static constexpr int HEAD_STAGES = 4;          // input ring: tiles whose rows are in flight or waiting for the MMA
+static constexpr int HEAD_OFF_TAPS = 0;        // HEAD_STAGES x 2 rows
+static constexpr int HEAD_OFF_W = HEAD_STAGES * 2 * HEAD_SLAB;
 static constexpr int HEAD_OFF_LUT = HEAD_OFF_W + 4 * HEAD_WTAP;
 static constexpr int HEAD_OFF_BAR = HEAD_OFF_LUT + 256;
 static constexpr int HEAD_SMEM = HEAD_OFF_BAR + 128;
 
-// 41 KB of shared memory and 128 TMEM columns per CTA: four CTAs per SM keep four tiles in flight
+// 44 KB of shared memory and 128 TMEM columns per CTA: four CTAs per SM keep four tiles in flight
 __global__ void __launch_bounds__(192, 4)
-k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][128][16], 32-byte swizzle
+k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][129][16], 32-byte swizzle
             const HeadParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + HEAD_OFF_BAR);
-  enum { TAP_FULL0 = 0, TAP_FULL1, TAP_EMPTY0, TAP_EMPTY1, D_FULL0, D_FULL1, D_EMPTY0, D_EMPTY1, W_FULL, NBARS };
+  enum { TAP_FULL0 = 0, TAP_EMPTY0 = TAP_FULL0 + HEAD_STAGES, D_FULL0 = TAP_EMPTY0 + HEAD_STAGES, D_FULL1, D_EMPTY0, D_EMPTY1,
+         W_FULL, NBARS };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
   uint8_t* slut = smem + HEAD_OFF_LUT;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    const int one[] = {TAP_FULL0, TAP_FULL1, TAP_EMPTY0, TAP_EMPTY1, D_FULL0, D_FULL1, W_FULL};
+    for (int b = 0; b < 2 * HEAD_STAGES; ++b) mbar_init(bar(TAP_FULL0 + b), 1);
+    const int one[] = {D_FULL0, D_FULL1, W_FULL};
     for (int b : one) mbar_init(bar(b), 1);
     mbar_init(bar(D_EMPTY0), 128);
     mbar_init(bar(D_EMPTY1), 128);
@@ -72,26 +79,25 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
     for (int k = 0; k < T; ++k) {
       const int tile = blockIdx.x + k * gridDim.x;
       const int n = tile >> 8, y = (tile & 255) >> 1, x0 = (tile & 1) * 128;
-      const int b = k & 1;
-      if (k >= 2) mbar_wait(bar(TAP_EMPTY0 + b), ((k >> 1) - 1) & 1);
-      mbar_expect_tx_e(bar(TAP_FULL0 + b), 4 * HEAD_TAP);
+      const int st = k % HEAD_STAGES;
+      if (k >= HEAD_STAGES) mbar_wait(bar(TAP_EMPTY0 + st), ((k / HEAD_STAGES) - 1) & 1);
+      mbar_expect_tx_e(bar(TAP_FULL0 + st), 2 * HEAD_ROW);
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        tma_load_4d_e(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP, &map_x, 0, x0 + (t & 1), y + (t >> 1), n,
-                    bar(TAP_FULL0 + b));
+      for (int di = 0; di < 2; ++di)
+        tma_load_4d_e(sbase + HEAD_OFF_TAPS + (st * 2 + di) * HEAD_SLAB, &map_x, 0, x0, y + di, n, bar(TAP_FULL0 + st));
     }
   } else if (warp == 1) {
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
-      const int b = k & 1;
-      mbar_wait(bar(TAP_FULL0 + b), (k >> 1) & 1);
+      const int b = k & 1, st = k % HEAD_STAGES;
+      mbar_wait(bar(TAP_FULL0 + st), (k / HEAD_STAGES) & 1);
       if (k >= 2) mbar_wait(bar(D_EMPTY0 + b), ((k >> 1) - 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < 4; ++t)
-        umma_bf16_e(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (b * 4 + t) * HEAD_TAP),
+        umma_bf16_e(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (st * 2 + (t >> 1)) * HEAD_SLAB + (t & 1) * 32),
                   smem_desc<32>(sbase + HEAD_OFF_W + t * HEAD_WTAP), IDESC, t != 0);
-      umma_commit_e(bar(TAP_EMPTY0 + b));
+      umma_commit_e(bar(TAP_EMPTY0 + st));
       umma_commit_e(bar(D_FULL0 + b));
     }
   } else {
@@ -162,7 +168,7 @@ bool head_build(uint8_t** out, const float* w, int C, int CP) {
 cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,
                              int num_sms, cudaStream_t s) {
   CUtensorMap mx;
-  if (!make_map_e1(&mx, x, B, 128, 256, 16)) return cudaErrorInvalidValue;
+  if (!make_map_box(&mx, x, B, 128, 256, 16, 129, 1)) return cudaErrorInvalidValue;
   HeadParams p{};
   p.num_tiles = B * 256;
   p.C = C;
