@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-latency", action="store_true")
     ap.add_argument("--skip-contour", action="store_true")
+    ap.add_argument("--skip-config5", action="store_true")
     ap.add_argument("--nccl-gather", action="store_true")
     ap.add_argument("--weights", default=WEIGHTS, choices=sorted(WEIGHT_FILES))
     ap.add_argument("--frames", default=FRAMES, choices=["scene", "noise"])
@@ -415,6 +416,33 @@ def main():
                    "cpu_opencv_ms_per_frame": cpu_ms, "bit_exact_vs_opencv_on_8_frames": exact,
                    "masks": "predict_binary labels of the benchmark batch"}
 
+    # ---- BASELINE config 5 (DeepLab 720p, bs 32): the forward is blocked (no graph, no weights), so only the
+    # post-processing is measured: label maps (32,720,1280) -> grids with a 720p calibration
+    config5 = None
+    if rank == 0 and world == 1 and not args.skip_config5:
+        from bugcar_image_segmentation_b200 import _lib
+        from oracle import bev_oracle
+        c5 = _lib.Context(local, 32)
+        calE = synth.calibration("E", 720, 1280)
+        wwE, whE = calE["output image size"]
+        c5.set_bev(calE["bev matrix"], 720, 1280, wwE, whE, calE["cm_per_px"])
+        hE, wE = c5.occgrid_shape(*GRID)
+        lab5 = np.stack([synth.label_map(500 + i, 3, 720, 1280) for i in range(32)])
+        d_lab5 = torch.from_numpy(lab5).cuda()
+        d_g5 = torch.empty((32, hE, wE), dtype=torch.int8, device="cuda")
+        run5 = lambda i: c5.occgrid(d_lab5, 32, *GRID, 0, 0, d_g5, stream.cuda_stream)
+        for i in range(3):
+            run5(i)
+        ms5 = timed(run5, 20) / 20
+        t0 = time.perf_counter()
+        want5 = [bev_oracle.occupancy_grid(lab5[i], calE["bev matrix"], wwE, whE, calE["cm_per_px"], *GRID, backend="cv2")
+                 for i in range(4)]
+        cpu5 = (time.perf_counter() - t0) / 4 * 1e3
+        config5 = {"what": "post-processing only (K9) on synthetic label maps (32,720,1280), calibration E",
+                   "frames_per_s": 32 / ms5 * 1e3, "ms_per_batch": ms5, "cpu_opencv_ms_per_frame": cpu5,
+                   "bit_exact_vs_cpu_on_4_frames": bool(np.array_equal(np.stack(want5), d_g5[:4].cpu().numpy()))}
+        c5.close()
+
     # ---- CPU baseline on a bounded sample (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -450,7 +478,8 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "latency_bs1": latency, "contour_filter": contour, "kernels": kernels,
+            "latency_bs1": latency, "contour_filter": contour, "config5_postprocessing": config5,
+            "kernels": kernels,
         }))
     if world > 1:
         dist.destroy_process_group()

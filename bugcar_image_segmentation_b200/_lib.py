@@ -37,6 +37,8 @@ SIGNATURES = {
     "bc_enet_block_output": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "bc_enet_labels": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "bc_argmax_lut": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "bc_occgrid_laserscan": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _vp, _vp, _vp]),
+    "bc_laser_tables": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
     "bc_contour_noise_removal": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "bc_set_contour_filter": (_i, [_vp, _i]),
     "bc_occgrid_shape": (_i, [_vp, _d, _d, _d, C.POINTER(_i), C.POINTER(_i)]),
@@ -176,6 +178,10 @@ class Context:
         self._ck(self.lib.bc_argmax_lut(self.h, _ptr(d_logits), B, Cn, H, W, _lut(lut), _ptr(d_labels),
                                         _ptr(stream)))
 
+    def occgrid_laserscan(self, d_labels, B, w_m, h_m, cell_m, binary, d_grid_plain, d_grid_laser, stream=None):
+        self._ck(self.lib.bc_occgrid_laserscan(self.h, _ptr(d_labels), B, float(w_m), float(h_m), float(cell_m),
+                                               int(binary), _ptr(d_grid_plain), _ptr(d_grid_laser), _ptr(stream)))
+
     def contour_noise_removal(self, d_seg, H, W, B, d_out, stream=None):
         self._ck(self.lib.bc_contour_noise_removal(self.h, _ptr(d_seg), int(H), int(W), int(B), _ptr(d_out),
                                                    _ptr(stream)))
@@ -224,6 +230,20 @@ class Context:
         """list of {"kernel", "launches", "ms", "bytes", "flops"} since set_profile(True)"""
         import json
         return json.loads(self.lib.bc_profile_json(self.h).decode())
+
+
+def laser_tables(Wc, Hc, binary):
+    """(fwd (pol_h, pol_w), inv (Hc, Wc)) int32 gather tables of the laserscan branch; host only."""
+    import numpy as np
+    lib = load()
+    pw, ph = _i(), _i()
+    rc = lib.bc_laser_tables(int(Wc), int(Hc), int(binary), C.byref(pw), C.byref(ph), None, None)
+    if rc != BC_OK:
+        raise BugcarError(rc, "bad grid shape")
+    fwd = np.empty((ph.value, pw.value), np.int32)
+    inv = np.empty((int(Hc), int(Wc)), np.int32)
+    lib.bc_laser_tables(int(Wc), int(Hc), int(binary), C.byref(pw), C.byref(ph), fwd.ctypes.data, inv.ctypes.data)
+    return fwd, inv
 
 
 def _lut(lut):

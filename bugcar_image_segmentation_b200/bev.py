@@ -112,13 +112,20 @@ class bev_transform_tools:
         assert shape == (self.input_width, self.input_height), \
             "current segmap size: {},the segmap's original size must be the same as the required input shape, which is {}" \
             .format(shape, (self.input_width, self.input_height))
-        if self.laserscan_like_occupancy_grid:
-            raise NotImplementedError("laserscan-like grids are not reproduced: the reference reads uninitialised "
-                                      "warpPolar output there (bev.py:145-164, 216-240)")
         torch, dev = runtime.torch_cuda(None if self._ctx is None else self._ctx.device)
         ctx = self._context()
         d_lab = runtime.to_device_u8(torch, ctx.device, segmap)
         hc, wc = ctx.occgrid_shape(w_m, h_m, cell_m)
+        if self.laserscan_like_occupancy_grid:
+            # bev.py:145-164 / 216-240 with the warpPolar outliers defined as 0 (the reference leaves them
+            # uninitialised); the binary variant returns the reference's 2-tuple (plain grid, laserscan grid)
+            if ros_layout:
+                raise NotImplementedError("ros_layout is not available for laserscan-like grids")
+            d_laser = torch.empty((hc, wc), dtype=torch.int8, device=d_lab.device)
+            d_plain = torch.empty((hc, wc), dtype=torch.int8, device=d_lab.device) if binary else None
+            ctx.occgrid_laserscan(d_lab, 1, w_m, h_m, cell_m, binary, d_plain, d_laser,
+                                  runtime.stream_handle(torch, ctx.device))
+            return (d_plain.cpu().numpy(), d_laser.cpu().numpy()) if binary else d_laser.cpu().numpy()
         out_shape = (wc, hc) if ros_layout else (hc, wc)
         d_grid = torch.empty(out_shape, dtype=torch.int8, device=d_lab.device)
         ctx.occgrid(d_lab, 1, w_m, h_m, cell_m, binary, ros_layout, d_grid, runtime.stream_handle(torch, ctx.device))

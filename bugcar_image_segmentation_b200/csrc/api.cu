@@ -139,6 +139,13 @@ struct bc_ctx {
   uint8_t* d_labels_cn = nullptr;     // filtered road masks of the binary pipeline [max_batch][256][512]
   int contour_filter = 0;
 
+  // ---- laserscan-like grids (bev.py:145-164, 216-240): gather tables per grid shape, scratch
+  struct LaserTab { int Wc, Hc, binary, pol_w, pol_h; int* d_fwd; int* d_inv; };
+  std::vector<LaserTab> laser_tabs;
+  uint8_t* laser_cells = nullptr;     // [B][Hc*Wc] plain grid / raw template
+  int* laser_first = nullptr;         // [B][pol_h]
+  size_t laser_cells_bytes = 0, laser_first_bytes = 0;
+
   // ---- multi-GPU gather
   int8_t* gather_base = nullptr;
   int rank = 0, world = 1;
@@ -891,7 +898,7 @@ int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int 
   g.ify = 1.0 / ((double)Hc / (double)occ_h_px);
   if (!with_table) return BC_OK;
   BevGeom key = g;
-  key.binary = key.ros_layout = 0;        // the coordinates do not depend on them
+  key.binary = key.ros_layout = key.raw_template = 0;        // the coordinates do not depend on them
   for (auto& kv : c->occ_tables)
     if (memcmp(&kv.first, &key, sizeof key) == 0) { g.table = kv.second; return BC_OK; }
   CU(cudaSetDevice(c->device));
@@ -1079,7 +1086,8 @@ void bc_destroy(bc_ctx* c) {
   for (auto e : c->copy_done) if (e) cudaEventDestroy(e);
   if (c->call_start) cudaEventDestroy(c->call_start);
   void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out, c->cn_scratch,
-                c->d_labels_cn};
+                c->d_labels_cn, c->laser_cells, c->laser_first};
+  for (auto& t : c->laser_tabs) { cudaFree(t.d_fwd); cudaFree(t.d_inv); }
   for (void* p : ps) if (p) cudaFree(p);
   delete c;
 }
@@ -1264,6 +1272,69 @@ int bc_set_contour_filter(bc_ctx* c, int enable) {
     if (!c->d_labels_cn) CU(cudaMalloc(&c->d_labels_cn, (size_t)c->max_batch * BC_NET_H * BC_NET_W));
   }
   c->contour_filter = enable ? 1 : 0;
+  return BC_OK;
+}
+
+int bc_occgrid_laserscan(bc_ctx* c, const uint8_t* d_labels, int B, double w_m, double h_m, double cell_m, int binary,
+                         int8_t* d_grid_plain, int8_t* d_grid_laser, void* stream) {
+  if (!c) return BC_ERR_ARG;
+  if (!d_labels || !d_grid_laser) return fail(c, BC_ERR_ARG, "null pointer");
+  if (B < 1 || B > 65535) return fail(c, BC_ERR_ARG, "batch size outside [1, 65535]");
+  BevGeom g;
+  int r = make_geom(c, w_m, h_m, cell_m, binary, 0, g);
+  if (r) return r;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // gather tables of this grid shape (host-built once, OpenCV's float arithmetic)
+  const bc_ctx::LaserTab* tab = nullptr;
+  for (auto& t : c->laser_tabs) if (t.Wc == g.Wc && t.Hc == g.Hc && t.binary == g.binary) tab = &t;
+  if (!tab) {
+    bc_ctx::LaserTab t{g.Wc, g.Hc, g.binary, 0, 0, nullptr, nullptr};
+    laser_polar_size(g.Wc, g.Hc, g.binary, &t.pol_w, &t.pol_h);
+    std::vector<int> fwd, inv;
+    laser_build_tables(g.Wc, g.Hc, t.pol_w, t.pol_h, fwd, inv);
+    CU(cudaMalloc(&t.d_fwd, fwd.size() * sizeof(int)));
+    CU(cudaMalloc(&t.d_inv, inv.size() * sizeof(int)));
+    CU(cudaMemcpy(t.d_fwd, fwd.data(), fwd.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_inv, inv.data(), inv.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->laser_tabs.push_back(t);
+    tab = &c->laser_tabs.back();
+  }
+  const size_t cells_bytes = (size_t)B * g.Hc * g.Wc, first_bytes = (size_t)B * tab->pol_h * sizeof(int);
+  if (cells_bytes > c->laser_cells_bytes) {
+    if (c->laser_cells) cudaFree(c->laser_cells);
+    c->laser_cells = nullptr; c->laser_cells_bytes = 0;
+    CU(cudaMalloc(&c->laser_cells, cells_bytes));
+    c->laser_cells_bytes = cells_bytes;
+  }
+  if (first_bytes > c->laser_first_bytes) {
+    if (c->laser_first) cudaFree(c->laser_first);
+    c->laser_first = nullptr; c->laser_first_bytes = 0;
+    CU(cudaMalloc(&c->laser_first, first_bytes));
+    c->laser_first_bytes = first_bytes;
+  }
+  // binary: the plain grid is the first element of the reference's tuple (bev.py:164) and the source of the
+  // polar search; three-way: the search runs on the resized template (values 0..3, bev.py:209-219)
+  uint8_t* cells = c->laser_cells;
+  if (binary && d_grid_plain) cells = (uint8_t*)d_grid_plain;
+  g.raw_template = binary ? 0 : 1;
+  L(c, "occgrid", (double)B * ((double)g.in_rows * g.in_cols + (double)g.Hc * g.Wc), 0, s,
+    [&] { launch_occgrid(d_labels, B, g, (int8_t*)cells, s); });
+  L(c, "laserscan", (double)B * 2.0 * g.Hc * g.Wc, 0, s,
+    [&] { launch_laser(cells, B, g.Wc, g.Hc, tab->pol_w, tab->pol_h, g.binary, tab->d_fwd, tab->d_inv, c->laser_first,
+                       d_grid_laser, s); });
+  c->launches += 1;
+  return check_launch(c, "occgrid_laserscan");
+}
+
+int bc_laser_tables(int Wc, int Hc, int binary, int* pol_w, int* pol_h, int* h_fwd, int* h_inv) {
+  if (Wc < 1 || Hc < 1 || !pol_w || !pol_h) return BC_ERR_ARG;
+  laser_polar_size(Wc, Hc, binary, pol_w, pol_h);
+  if (!h_fwd && !h_inv) return BC_OK;                  // size query
+  std::vector<int> fwd, inv;
+  laser_build_tables(Wc, Hc, *pol_w, *pol_h, fwd, inv);
+  if (h_fwd) memcpy(h_fwd, fwd.data(), fwd.size() * sizeof(int));
+  if (h_inv) memcpy(h_inv, inv.data(), inv.size() * sizeof(int));
   return BC_OK;
 }
 

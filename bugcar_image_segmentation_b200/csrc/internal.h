@@ -65,6 +65,7 @@ struct BevGeom {            // kernel parameter block for K9 (passed by value)
   int crop_w, crop_h;
   int Wc, Hc;               // grid cells
   int binary, ros_layout;
+  int raw_template;         // 1: write the resized template value (0..3) instead of the int8 map (laserscan branch)
   double ifx, ify;          // nearest-resize source step (cv::resize INTER_NEAREST, fp64)
   const uint4* table;       // device table of k_occ_table for this geometry ([25][Hc*Wc]); host-side cache key has it null
 };
@@ -156,5 +157,13 @@ void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grid
 size_t contour_scratch_bytes(int B, int H, int W);
 int contour_launch_count();
 void launch_contour_noise_removal(const uint8_t* seg, int H, int W, int B, uint8_t* out, void* scratch, cudaStream_t s);
+
+
+// ------------------------------------------------------------------ launchers (laser.cu)
+// laserscan-like grids (bev.py:145-164, 216-240): polar image size, host-built gather tables, per-batch kernels
+void laser_polar_size(int Wc, int Hc, int binary, int* pol_w, int* pol_h);
+void laser_build_tables(int Wc, int Hc, int pol_w, int pol_h, std::vector<int>& fwd, std::vector<int>& inv);
+void launch_laser(const uint8_t* cells, int B, int Wc, int Hc, int pol_w, int pol_h, int binary, const int* d_fwd,
+                  const int* d_inv, int* d_first, int8_t* out, cudaStream_t s);
 
 }  // namespace bc

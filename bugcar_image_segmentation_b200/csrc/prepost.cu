@@ -294,7 +294,9 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
     }
     if (occupied && !opened) v = 2;                   // bev.py:203-205
     int out;
-    if (g.binary) {
+    if (g.raw_template) {
+      out = v;                                        // laserscan branch: the template itself (bev.py:209-212)
+    } else if (g.binary) {
       int m = (v * 100) & 255;                        // uint8 * 100 (bev.py:139-142)
       out = (m == 0) ? 255 : ((200 - m) & 255);       // bev.py:143-144
     } else {

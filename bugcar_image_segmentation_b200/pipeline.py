@@ -23,7 +23,8 @@ class FramePipeline:
     def __init__(self, model, bev, grid_width_in_m, grid_height_in_m, cell_size_in_m, binary=False,
                  ros_layout=False, contour_filter=False):
         if bev.laserscan_like_occupancy_grid:
-            raise NotImplementedError("laserscan-like grids are not reproduced (bev.py:216-240)")
+            raise NotImplementedError("the fused pipeline writes ordinary grids; for laserscan-like grids "
+                                      "(bev.py:145-164, 216-240) call predict + create_occupancy_grid[_binary]")
         self.model, self.bev = model, bev
         self.ctx = bev._context(model.ctx)              # the model's context now carries the calibration
         self.w_m, self.h_m, self.cell_m = float(grid_width_in_m), float(grid_height_in_m), float(cell_size_in_m)

@@ -135,6 +135,24 @@ int bc_occgrid_shape(bc_ctx* ctx, double w_m, double h_m, double cell_m, int* Hc
 int bc_occgrid(bc_ctx* ctx, const uint8_t* d_labels, int B, double w_m, double h_m,
                double cell_m, int binary, int ros_layout, int8_t* d_grids, void* stream);
 
+/* Laserscan-like grids (the `is_laserscan` branch, bev.py:145-164 binary / bev.py:216-240 three-way): only
+ * the first obstacle along each ray from the camera (grid centre (Wc/2 - 1, Hc)) is kept, behind it
+ * the grid is unknown.  The reference runs its two cv2.warpPolar calls without WARP_FILL_OUTLIERS and
+ * so reads uninitialised memory wherever a ray leaves the grid; here those pixels are 0, i.e. the
+ * result equals the reference's with that flag set.  binary = 1: d_grid_plain (may be NULL) receives
+ * the ordinary binary grid and d_grid_laser the laserscan one -- the reference's 2-tuple (bev.py:164);
+ * binary = 0: d_grid_plain is ignored.  Grids are int8 (B,Hc,Wc).  Allocates on first use of a grid
+ * shape / a larger batch: call once outside stream capture. */
+int bc_occgrid_laserscan(bc_ctx* ctx, const uint8_t* d_labels, int B, double w_m, double h_m,
+                         double cell_m, int binary, int8_t* d_grid_plain, int8_t* d_grid_laser,
+                         void* stream);
+
+/* Host-only (no GPU, no context): the two gather tables bc_occgrid_laserscan builds for a (Wc,Hc) grid,
+ * i.e. the coordinate maps of cv2.warpPolar(..., WARP_POLAR_LINEAR) and (..., WARP_INVERSE_MAP) after
+ * nearest-neighbour rounding.  h_fwd [pol_h][pol_w] -> flat grid cell or -1, h_inv [Hc][Wc] -> flat polar
+ * pixel or -1; pass both NULL to query the polar size.  For tests and for hosts that post-process grids. */
+int bc_laser_tables(int Wc, int Hc, int binary, int* pol_w, int* pol_h, int* h_fwd, int* h_inv);
+
 /* ---- contour_noise_removal  (image_processing_utils.py:4-44) ----------------------------- */
 /* d_seg uint8 (B,H,W) road masks (non-zero = road, as ENET.predict_binary returns them) ->
  * d_out uint8 (B,H,W) in {0,1}: k x k close with k = int(min(H,W)/50) (:6-9), then every contour

@@ -39,6 +39,42 @@ class _Anything(types.ModuleType):
         return _Anything(self.__name__ + "()")
 
 
+class _GroupBy:
+    """numpy_indexed.group_by(keys).min(values) -> (unique keys, per-key minimum), the only use
+    the reference makes of the package (bev.py:156, :229); numpy_indexed is not installed."""
+
+    def __init__(self, keys):
+        import numpy as np
+        self.keys = np.asarray(keys)
+
+    def min(self, values):
+        import numpy as np
+        values = np.asarray(values)
+        uniq = np.unique(self.keys)
+        return uniq, np.array([values[self.keys == k].min() for k in uniq])
+
+
+def deterministic_laserscan(ref):
+    """Make the reference's laserscan branch a function of its input: OR WARP_FILL_OUTLIERS into its
+    two cv2.warpPolar calls (bev.py:148,160,219,235 leave outliers uninitialised) and give it the
+    group_by().min it imports from the absent numpy_indexed.  Returns an undo callable."""
+    import cv2
+    orig = cv2.warpPolar
+
+    def filled(src, dsize, center, maxRadius, flags):
+        return orig(src, dsize, center, maxRadius, flags | cv2.WARP_FILL_OUTLIERS)
+
+    cv2.warpPolar = filled
+    old_gb = getattr(ref.bev.npi, "group_by", None)
+    ref.bev.npi.group_by = _GroupBy
+
+    def undo():
+        cv2.warpPolar = orig
+        if old_gb is not None:
+            ref.bev.npi.group_by = old_gb
+    return undo
+
+
 def load():
     """Return the reference as the package ``reference`` (modules bev, models,
     utils, image_processing_utils importable as attributes)."""

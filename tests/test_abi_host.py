@@ -151,3 +151,18 @@ def test_state_dict_converter_roundtrip(tmp_path, synthetic_weights):
                         "--classes", str(nc)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert dst.read_bytes() == blob
+
+
+def test_laser_tables_match_oracle():
+    """bc_laser_tables is host-only: the C++ restatement of cv::warpPolar's coordinate maps equals the
+    oracle's (which tests/test_oracle_laser.py pins against cv2.warpPolar itself)."""
+    from bugcar_image_segmentation_b200 import _lib
+    from oracle import laser_oracle
+    for wc, hc in [(100, 100), (80, 60), (101, 77), (40, 100), (32, 24)]:
+        for binary in (0, 1):
+            fwd, inv = _lib.laser_tables(wc, hc, binary)
+            ph, pw = fwd.shape
+            centre, radius = (wc / 2 - 1, hc), max(wc, hc)
+            assert binary or (pw, ph) == laser_oracle.polar_dsize(radius)
+            assert np.array_equal(fwd, laser_oracle.forward_map(pw, ph, centre[0], centre[1], radius, wc, hc))
+            assert np.array_equal(inv, laser_oracle.inverse_map(wc, hc, centre[0], centre[1], radius, pw, ph))

@@ -146,8 +146,9 @@ def test_grid_error_behaviour(tmp_path):
     with pytest.raises(AssertionError):                     # bev.py:169-170
         bev.create_occupancy_grid(np.zeros((100, 100), np.uint8), 10.0, 10.0, 0.1)
     bev.laserscan_like_occupancy_grid = True
-    with pytest.raises(NotImplementedError):
-        bev.create_occupancy_grid(np.zeros((256, 512), np.uint8), 10.0, 10.0, 0.1)
+    with pytest.raises(NotImplementedError):                # the ROS layout exists for ordinary grids only
+        bev.create_occupancy_grid_ros(np.zeros((256, 512), np.uint8), 10.0, 10.0, 0.1)
+    bev.laserscan_like_occupancy_grid = False
     raw = _lib.Context(0, 1)
     with pytest.raises(_lib.BugcarError) as e:              # calibration not set
         raw.occgrid_shape(10.0, 10.0, 0.1)

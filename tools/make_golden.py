@@ -11,6 +11,8 @@ regenerates them); large outputs are stored as sha256 + a strided sample.
   resize.npz       cv2.resize(bgr,(512,256)) hashes                     (models.py:87)
   argmax.npz       logits with ties -> labels (np.argmax == tf.math.argmax tie-break; models.py:55-58)
   contour.npz      reference contour_noise_removal on synth.road_mask seeds (image_processing_utils.py:4-44)
+  laser.npz        reference laserscan-like grids (bev.py:145-164, 216-240) with WARP_FILL_OUTLIERS patched
+                   into its two warpPolar calls (the unpatched branch reads uninitialised memory)
   enet.npz         oracle (torch fp32) logits sample for the synthetic weights: PARITY UNPINNED,
                    guards the oracle against drift only
 """
@@ -117,6 +119,24 @@ def main():
         cn[f"out_{s_}"] = np.packbits(out)
         cn[f"closed_sha_{s_}"] = np.array(sha(cv2.morphologyEx(m, cv2.MORPH_CLOSE, np.ones((k, k), np.uint8))))
     np.savez_compressed(os.path.join(OUT, "contour.npz"), **cn)
+
+    # ---- laserscan-like grids (8f-3), reference made deterministic by refstub.deterministic_laserscan
+    undo = refstub.deterministic_laserscan(ref)
+    ls = {"cals": np.array(["A", "B"]), "grid_args": np.array([[10.0, 10.0, 0.1], [8.0, 6.0, 0.25], [6.0, 9.0, 0.2]]),
+          "seeds": np.arange(3)}
+    for name in ls["cals"]:
+        cal = dict(synth.calibration(str(name)), is_laserscan=True)
+        bev = _ref_bev(ref, cal)
+        for ai, args_ in enumerate(ls["grid_args"]):
+            for s_ in ls["seeds"]:
+                lab3 = synth.label_map(300 + int(s_), 3, block=16 if s_ else 32)
+                lab2 = synth.label_map(400 + int(s_), 2, block=16 if s_ else 32)
+                ls[f"g3_{name}_{ai}_{s_}"] = bev.create_occupancy_grid(lab3, *args_)
+                plain, laser = bev.create_occupancy_grid_binary(lab2, *args_)
+                ls[f"g2p_{name}_{ai}_{s_}"] = plain
+                ls[f"g2l_{name}_{ai}_{s_}"] = laser
+    undo()
+    np.savez_compressed(os.path.join(OUT, "laser.npz"), **ls)
 
     # ---- ENet oracle self-pin
     with open(os.path.join(ROOT, "pretrained_models", "enet_synthetic_seed42.bcw"), "rb") as f:
