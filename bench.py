@@ -416,6 +416,29 @@ def main():
                    "cpu_opencv_ms_per_frame": cpu_ms, "bit_exact_vs_opencv_on_8_frames": exact,
                    "masks": "predict_binary labels of the benchmark batch"}
 
+    # ---- laserscan-like grids from the benchmark's labels (deterministic re-specification)
+    laser = None
+    if rank == 0 and world == 1 and not args.skip_contour:
+        from oracle import bev_oracle, laser_oracle
+        d_lab3 = torch.empty((B, 256, 512), dtype=torch.uint8, device="cuda")
+        pipe.run_device(dev_sets[0], d_grids, d_labels=d_lab3)
+        d_laser = torch.empty_like(d_grids)
+        run_l = lambda i: model.ctx.occgrid_laserscan(d_lab3, B, *GRID, 0, None, d_laser, stream.cuda_stream)
+        for i in range(3):
+            run_l(i)
+        ms_l = timed(run_l, 10) / 10
+        labs = d_lab3[:4].cpu().numpy()
+        t0 = time.perf_counter()
+        want_l = []
+        for m in labs:
+            _, templ = bev_oracle.occupancy_grid(m, cal["bev matrix"], *cal["output image size"], cal["cm_per_px"], *GRID,
+                                                 backend="cv2", return_template=True)
+            want_l.append(laser_oracle.laserscan_3way(templ))
+        cpu_l = (time.perf_counter() - t0) / len(labs) * 1e3
+        laser = {"what": "labels -> laserscan-like grid (bc_occgrid_laserscan, three-way), bs %d" % B,
+                 "frames_per_s": B / ms_l * 1e3, "ms_per_batch": ms_l, "cpu_port_ms_per_frame": cpu_l,
+                 "bit_exact_vs_cpu_on_4_frames": bool(np.array_equal(np.stack(want_l), d_laser[:4].cpu().numpy()))}
+
     # ---- BASELINE config 5 (DeepLab 720p, bs 32): the forward is blocked (no graph, no weights), so only the
     # post-processing is measured: label maps (32,720,1280) -> grids with a 720p calibration
     config5 = None
@@ -478,7 +501,7 @@ def main():
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "latency_bs1": latency, "contour_filter": contour, "config5_postprocessing": config5,
+            "latency_bs1": latency, "contour_filter": contour, "laserscan": laser, "config5_postprocessing": config5,
             "kernels": kernels,
         }))
     if world > 1:
