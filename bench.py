@@ -214,6 +214,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there
+    # when NCCL_DEBUG is set) go to stderr until the result is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     B = args.batch
@@ -487,6 +492,9 @@ def main():
                          "(torch fp32 ENet + OpenCV pre/post)",
                "grid_cell_agreement_bf16_vs_cpu_fp32": same}
 
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
