@@ -22,9 +22,9 @@ from . import runtime
 class FramePipeline:
     def __init__(self, model, bev, grid_width_in_m, grid_height_in_m, cell_size_in_m, binary=False,
                  ros_layout=False, contour_filter=False):
-        if bev.laserscan_like_occupancy_grid:
-            raise NotImplementedError("the fused pipeline writes ordinary grids; for laserscan-like grids "
-                                      "(bev.py:145-164, 216-240) call predict + create_occupancy_grid[_binary]")
+        self.laserscan = bool(bev.laserscan_like_occupancy_grid)      # bev.py:145-164 / 216-240, outliers = 0
+        if self.laserscan and ros_layout:
+            raise NotImplementedError("ros_layout is not available for laserscan-like grids")
         self.model, self.bev = model, bev
         self.ctx = bev._context(model.ctx)              # the model's context now carries the calibration
         self.w_m, self.h_m, self.cell_m = float(grid_width_in_m), float(grid_height_in_m), float(cell_size_in_m)
@@ -49,6 +49,8 @@ class FramePipeline:
         gather buffer selected with ``sharding.PeerGather.use`` (returns None)."""
         torch = self._torch
         B, h, w, _ = d_frames.shape
+        if self.laserscan:
+            return self._run_laserscan(d_frames, d_grids, d_labels, to_gather)
         if to_gather:
             if B > self.ctx.max_batch:
                 raise ValueError("to_gather needs the batch in one call (B <= max_batch)")
@@ -66,6 +68,27 @@ class FramePipeline:
                               d_grids[b0:b0 + n], s)
         return d_grids
 
+    def _run_laserscan(self, d_frames, d_grids, d_labels, to_gather):
+        """frames -> labels (the fused pipeline, whose ordinary grid is discarded) -> laserscan-like grid.
+        With binary=True the result is the laserscan grid, the second element of the reference's tuple."""
+        torch = self._torch
+        if to_gather:
+            raise NotImplementedError("peer-gathered grids are ordinary grids")
+        B, h, w, _ = d_frames.shape
+        s = runtime.stream_handle(torch, self.device)
+        if d_grids is None:
+            d_grids = torch.empty((B, self.Hc, self.Wc), dtype=torch.int8, device=d_frames.device)
+        if d_labels is None:
+            d_labels = torch.empty((B, 256, 512), dtype=torch.uint8, device=d_frames.device)
+        step = self.ctx.max_batch
+        for b0 in range(0, B, step):
+            n = min(step, B - b0)
+            self.ctx.pipeline(d_frames[b0:b0 + n], h, w, n, self.lut, self.w_m, self.h_m, self.cell_m, self.binary, 0,
+                              d_labels[b0:b0 + n], d_grids[b0:b0 + n], s)
+            self.ctx.occgrid_laserscan(d_labels[b0:b0 + n], n, self.w_m, self.h_m, self.cell_m, self.binary, None,
+                                       d_grids[b0:b0 + n], s)
+        return d_grids
+
     def __call__(self, frames):
         """frames: uint8 (B,h,w,3) or (h,w,3) BGR host array -> int8 (B,*grid_shape) host
         array.  Stages through pinned buffers: H2D, the graph, D2H, one sync."""
@@ -79,6 +102,10 @@ class FramePipeline:
             self._pinned_in = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)
             self._pinned_out = torch.empty((B,) + self.grid_shape, dtype=torch.int8, pin_memory=True)
         self._pinned_in.numpy()[...] = frames
+        if self.laserscan:
+            d = self._run_laserscan(self._pinned_in.to(f"cuda:{self.device}", non_blocking=True), None, None, False)
+            out = d.cpu().numpy()
+            return out[0] if single else out
         s = runtime.stream_handle(torch, self.device)
         step = self.ctx.max_batch
         for b0 in range(0, B, step):

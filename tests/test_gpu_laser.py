@@ -71,3 +71,28 @@ def test_no_obstacle():
     road = np.ones((256, 512), np.uint8)                       # everything road: nothing to hit
     g3 = bev.create_occupancy_grid(road, 10.0, 10.0, 0.1)
     assert not (g3 == 100).any()
+
+
+def test_fused_pipeline_laserscan():
+    """FramePipeline on a laserscan calibration == its own labels -> create_occupancy_grid[_binary] on that calibration."""
+    import os
+    import torch
+    from bugcar_image_segmentation_b200 import synth
+    from bugcar_image_segmentation_b200.models import ENET
+    from bugcar_image_segmentation_b200.pipeline import FramePipeline
+    from conftest import ROOT
+    bev, _ = _bev("A")
+    model = ENET(os.path.join(ROOT, "pretrained_models", "enet_synthetic_trained.bcw"), device=0, max_batch=2)
+    frames = np.stack([synth.region_frame(70 + i)[0] for i in range(3)])
+    for binary in (False, True):
+        pipe = FramePipeline(model, bev, 10.0, 10.0, 0.1, binary=binary)
+        d_lab = torch.empty((3, 256, 512), dtype=torch.uint8, device="cuda")
+        got = pipe.run_device(torch.from_numpy(frames).cuda(), d_labels=d_lab).cpu().numpy()   # 3 frames, max_batch 2
+        lab = d_lab.cpu().numpy()
+        assert np.array_equal(got, pipe(frames))                    # host entry point, same grids
+        for i in range(3):
+            if binary:
+                want = bev.create_occupancy_grid_binary(lab[i], 10.0, 10.0, 0.1)[1]
+            else:
+                want = bev.create_occupancy_grid(lab[i], 10.0, 10.0, 0.1)
+            assert np.array_equal(got[i], want), (binary, i)
