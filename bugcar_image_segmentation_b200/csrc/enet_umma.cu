@@ -38,6 +38,7 @@ struct UmmaParams {
   int rows_per_tile;    // image rows a tile spans (128 / W)
   int ntaps;
   int8_t dy[9], dx[9];
+  int rowslab;          // 1: 3x3 dilation-1 conv on a one-row tile: 3 row loads of 130 pixels, kx through shifted descriptors
   int has_next;         // 1: compute the next block's projection from the y tile
   bf16* out_small;      // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
   const uint8_t* wblob; // packed weights, exact shared-memory image (see UmmaSmem)
@@ -74,6 +75,9 @@ struct UmmaSmem {
   static constexpr int THREADS = 128 + 128 * NG;
   static constexpr int RB = CI * 2;
   static constexpr int TAP_BYTES = 128 * RB;        // one A tap tile
+  // ring slot: a tap tile, or (row-slab mode, CI = 16) one image row of 128 + 2 pixels, padded to the 32-byte-swizzle repeat
+  static constexpr int ROW_BYTES = 130 * RB;
+  static constexpr int SLOT_BYTES = CI == 16 ? 17 * 256 : TAP_BYTES;
   static constexpr int XSUB = 128 * 128;            // one 64-channel sub-tile of x / y
   static constexpr int NSUB = C / 64;
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
@@ -86,7 +90,7 @@ struct UmmaSmem {
   static constexpr int OFF_X = 0;
   static constexpr int OFF_R = OFF_X + NY * XBUF;
   static constexpr int OFF_TAPS = OFF_R + NX * RBUF;
-  static constexpr int OFF_E2 = OFF_TAPS + NRING * TAP_BYTES;         // one e2 tile per group
+  static constexpr int OFF_E2 = ((OFF_TAPS + NRING * SLOT_BYTES + 1023) / 1024) * 1024;   // one e2 tile per group
   static constexpr int OFF_W = OFF_E2 + (CONV ? 0 : NG) * TAP_BYTES;  // weight image starts here
   static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
   static constexpr int W_LOAD = CONV ? 9 * Wt::W2_TAP : Wt::W_BYTES;  // bytes of the weight image this kernel needs
@@ -191,10 +195,20 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     const int dn = (int)gridDim.x / p.tiles_per_frame, dty = (int)gridDim.x % p.tiles_per_frame;
     for (int k = 0; k < T; ++k) {
       const int y0 = ty * p.rows_per_tile;
+      if (CI == 16 && p.rowslab) {
+        // one-row tiles: the three taps of a kernel row are the same 130-pixel row slab read at 0 / 1 / 2 pixels
+        // offset (map_e1's box is 130 pixels wide here): 3 loads and a third of the L2 -> SM bytes per tile
+        for (int ky = 0; ky < 3; ++ky) {
+          if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
+          mbar_expect_tx_e(bar(S::TAP_FULL + slot), S::ROW_BYTES);
+          tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, -1, y0 + ky - 1, n, bar(S::TAP_FULL + slot));
+          if (++slot == S::NRING) { slot = 0; ++round; }
+        }
+      } else
       for (int t = 0; t < p.ntaps; ++t) {
         if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
         mbar_expect_tx_e(bar(S::TAP_FULL + slot), S::TAP_BYTES);
-        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::TAP_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
+        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
         if (++slot == S::NRING) { slot = 0; ++round; }
       }
       n += dn; ty += dty;
@@ -208,12 +222,24 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     for (int k = 0; k < T; ++k) {
       const int g = k % NG;
       if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+      if (CI == 16 && p.rowslab) {
+        for (int ky = 0; ky < 3; ++ky) {
+          mbar_wait(bar(S::TAP_FULL + slot), round & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)                  // the swizzle follows the absolute address: a 32-byte shift is legal
+            umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + kx * 2),
+                        dB0 + (uint64_t)((ky * 3 + kx) * (Wt::W2_TAP >> 4)), IDESC_CONV, (ky | kx) != 0);
+          umma_commit_e(bar(S::TAP_EMPTY + slot));
+          if (++slot == S::NRING) { slot = 0; ++round; }
+        }
+      } else
       for (int t = 0; t < p.ntaps; ++t) {
         mbar_wait(bar(S::TAP_FULL + slot), round & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::TAP_BYTES >> 4) + kk * 2),
+          umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + kk * 2),
                       dB0 + (uint64_t)(t * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (t | kk) != 0);
         umma_commit_e(bar(S::TAP_EMPTY + slot));          // slot reusable once these MMAs retire
         if (++slot == S::NRING) { slot = 0; ++round; }
@@ -546,7 +572,11 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
   using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
   CUtensorMap me1, mx, my;
-  if (!make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
+  // row-slab mode: a plain 3x3 conv (dilation 1, taps in row-major order) whose 128-pixel tile is one image row
+  bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && getenv("BC_NO_ROWSLAB") == nullptr &&
+                 (has_next || getenv("BC_ROWSLAB_ALL") != nullptr);
+  for (int t = 0; rowslab && t < 9; ++t) rowslab = taps.dy[t] == t / 3 - 1 && taps.dx[t] == t % 3 - 1;
+  if (rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1) : !make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
   if (S::NARROW) {
     if (!make_map_rows(&mx, x, px, CRES, 128, S::RES_RB)) return cudaErrorInvalidValue;
@@ -563,6 +593,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) { p.dy[t] = taps.dy[t]; p.dx[t] = taps.dx[t]; }
   if ((conv_only != 0) != CONV) return cudaErrorInvalidValue;
+  p.rowslab = rowslab ? 1 : 0;
   p.has_next = has_next;
   p.out_small = out_small;
   p.wblob = pk.wblob;
