@@ -101,7 +101,7 @@ struct UmmaSmem {
                        E2_FULL = D1_EMPTY + NG, D2_FULL = E2_FULL + NG, Y_FULL = D2_FULL + NG, D3_FULL = Y_FULL + NG,
                        W_FULL = D3_FULL + NG, TAP_FULL = W_FULL + 1, TAP_EMPTY = TAP_FULL + NRING,
                        NBARS = TAP_EMPTY + NRING;
-  static_assert(NBARS * 8 + 8 <= 1024, "barrier block");
+  static_assert(NBARS * 8 + 8 + 4 * NX <= 1024, "barrier block");
   // 227 KB per CTA, 228 KB per SM with 1 KB reserved per resident CTA; + 1 KB alignment slack
   static_assert(TOTAL + 1024 <= 232448 && (TOTAL + 2048) * MINB <= 233472, "shared memory budget");
   // TMEM columns: every group owns a D1 / D2 / D3 accumulator
@@ -146,6 +146,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[S::NBARS];
+  uint32_t* xfills = tmem_slot + 2;                    // [NX] refills issued per x buffer (see epilogue 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup: barriers, weights + parameters to smem (two bulk copies), TMEM
@@ -156,6 +157,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
                             (i >= S::Y_FULL && i < S::Y_FULL + NG);
       mbar_init(bar(i), by_group ? 128 : 1);
     }
+    for (int i = 0; i < NX; ++i) xfills[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar(S::W_FULL), S::W_LOAD);
     bulk_load(sbase + S::OFF_W, p.wblob, S::W_LOAD, bar(S::W_FULL));
@@ -321,6 +323,18 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       const int xb = k % NX;
       uint8_t* yt = smem + S::OFF_X + (NARROW ? grp : xb) * S::XBUF;
       const uint8_t* rt = smem + S::OFF_R + xb * S::RBUF;         // narrow residual tile
+      // The x ring is shared by the groups, and a parity wait cannot tell "fill j done" from "fill j-1 still
+      // pending": a group that runs two tiles ahead of the other one (nothing orders them when there is no
+      // projection stage) would sail through, read the previous tile's x and then re-arm a barrier whose
+      // phase is still open (a trap).  So the storer publishes how many refills it has issued per buffer and
+      // the consumer checks that its fill exists before trusting the parity (almost always true at once).
+      if (k >= NX) {
+        const uint32_t need = (uint32_t)(k / NX);
+        uint32_t have;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(&xfills[xb])) : "memory");
+        } while (have < need);
+      }
       mbar_wait(bar(S::X_FULL + xb), (uint32_t)(k / NX) & 1);
       mbar_wait(bar(S::D2_FULL + grp), par);
       tc_fence_after();
@@ -363,6 +377,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
             const int nt = blockIdx.x + (k + NX) * gridDim.x;
             mbar_expect_tx(bar(S::X_FULL + xb), S::RBUF);
             tma_load_2d(sbase + S::OFF_R + xb * S::RBUF, &map_x, 0, nt * 128, bar(S::X_FULL + xb));
+            asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&xfills[xb])), "r"((uint32_t)((k + NX) / NX)) : "memory");
           }
         }
       }
@@ -393,6 +408,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
             mbar_expect_tx(bar(S::X_FULL + xb), S::XBUF);
             for (int s = 0; s < S::NSUB; ++s)
               tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb));
+            asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&xfills[xb])), "r"((uint32_t)((k + NX) / NX)) : "memory");
           }
         }
       }
@@ -573,8 +589,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
   CUtensorMap me1, mx, my;
   // row-slab mode: a plain 3x3 conv (dilation 1, taps in row-major order) whose 128-pixel tile is one image row
-  bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && getenv("BC_NO_ROWSLAB") == nullptr &&
-                 (has_next || getenv("BC_ROWSLAB_ALL") != nullptr);
+  bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && getenv("BC_NO_ROWSLAB") == nullptr;
   for (int t = 0; rowslab && t < 9; ++t) rowslab = taps.dy[t] == t / 3 - 1 && taps.dx[t] == t % 3 - 1;
   if (rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1) : !make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
