@@ -361,10 +361,13 @@ def main():
             k["tflops"] = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else 0.0
         kernels.sort(key=lambda k: -k["ms"])
         top = kernels[0]
-        traffic = None      # dram bytes per launch of that kernel from the committed ncu --set full capture
+        traffic = None      # dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json)
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get(top["kernel"], {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            for k in kernels:
+                k["dram_bytes_per_launch_ncu"] = tj.get(k["kernel"], {}).get("dram_bytes_per_launch")
+            traffic = top.get("dram_bytes_per_launch_ncu")
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
                     "frac": top["gbs"] / hbm, "traffic": traffic, "peak_source": which,
                     "share_of_step": top["share"], "avg_launch_us": top["ms"] * 1e3 / top["launches"],
