@@ -629,6 +629,11 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
   int H = 128, W = 256;   // resolution of X
   if (stop_after == -1) { launch_export_nchw<T>(X, dump, n, 16, H, W, s); return BC_OK; }
   int block_index = 0;
+  // direction in which the tensor now in X was written; a tcgen05 bottleneck launch walks the other way
+  // (kernels without a reverse walk run forward)
+  static const bool snake = getenv("BC_NO_SNAKE") == nullptr;
+  int x_dir = 0;
+  auto flip_dir = [&]() { x_dir = snake ? !x_dir : 0; g_umma_reverse = x_dir; };
   bool e1_ready = false;    // E1 already holds this block's projection (written by the previous tcgen05 kernel)
   const Taps t1 = taps_for(1, 1, 1);
   // conv launch with its algorithmic traffic: input + output (+ residual) activations
@@ -655,7 +660,8 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 pooling launch: ") + cudaGetErrorString(ce));
           L(c, b.cout == 64 ? "umma_down64" : "umma_down128", px * (cip + b.cin + b.cout + b.um_a.CN) * esz,
             2.0 * px * (9.0 * b.ci * b.ci + (double)b.ci * b.cout + (double)b.cout * b.um_a.CN), s,
-            [&] { ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)P, (bf16*)Y, (bf16*)E2, n, H, W, taps_for(3, 3, 1), 0, 1,
+            [&] { x_dir = 0; flip_dir();      // the pooling kernel above wrote P / E1 front to back
+                  ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)P, (bf16*)Y, (bf16*)E2, n, H, W, taps_for(3, 3, 1), 0, 1,
                                    c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 down-sampling launch: ") + cudaGetErrorString(ce));
           std::swap(E1, E2);          // e1' of the next block was written to E2
@@ -678,6 +684,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           cudaError_t ce = cudaSuccess;
           const int has_next = (b.kind == 1 ? b.um_a : b.um_b).has_next ? 1 : 0;
           const double io = px * (2.0 * b.cin + b.ci * (1 + has_next)) * esz;
+          flip_dir();                   // both launches of an asymmetric block walk the same way
           if (b.kind == 1) {
             L(c, b.cin == 64 ? "umma_bottleneck64" : "umma_bottleneck128", io,
               2.0 * px * (9.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
@@ -734,6 +741,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 upsampling launch: ") + cudaGetErrorString(ce));
           e1_ready = has_next != 0;
           done = true;
+          x_dir = 0;                    // the upsampling kernel walks front to back
         }
       }
       if (!done) {

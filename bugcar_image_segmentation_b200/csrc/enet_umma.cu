@@ -38,6 +38,7 @@ struct UmmaParams {
   int rows_per_tile;    // image rows a tile spans (128 / W)
   int ntaps;
   int8_t dy[9], dx[9];
+  int reverse;          // 1: walk the tiles from the last to the first (see launch_one: L2 reuse between consecutive kernels)
   int rowslab;          // 1: 3x3 dilation-1 conv on a one-row tile: 3 row loads of 130 pixels, kx through shifted descriptors
   int has_next;         // 1: compute the next block's projection from the y tile
   bf16* out_small;      // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
@@ -173,6 +174,12 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   constexpr uint32_t IDESC_CONV = instr_desc(128, CI), IDESC_EXP = instr_desc(128, C), IDESC_PROJ = instr_desc(128, CN);
   const int T = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // my tiles
   constexpr bool full = !CONV;
+  // k-th tile of this CTA; consecutive kernels walk in opposite directions so that a kernel starts on the
+  // tiles its predecessor wrote last (still in L2)
+  auto tile_of = [&](int k) {
+    const int t = (int)blockIdx.x + k * (int)gridDim.x;
+    return p.reverse ? p.num_tiles - 1 - t : t;
+  };
 
   // Service warps run their loops convergently (all 32 lanes) and elect one lane per instruction
   // inside the asm (umma_common.cuh): no divergence, no per-lane operand recomputation.
@@ -181,7 +188,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     // ============================================================ TMA producer (conv taps)
     if (full)                                            // first NX residual tiles; the rest are
       for (int k = 0; k < T && k < NX; ++k) {            // requested by the thread that frees a buffer
-        const int tile = blockIdx.x + k * gridDim.x;
+        const int tile = tile_of(k);
         if constexpr (NARROW) {
           mbar_expect_tx_e(bar(S::X_FULL + k), S::RBUF);
           tma_load_2d_e(sbase + S::OFF_R + k * S::RBUF, &map_x, 0, tile * 128, bar(S::X_FULL + k));
@@ -193,7 +200,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       }
     int slot = 0, round = 0;
     // (frame, tile-in-frame) of the current tile, advanced without divisions
-    int n = (int)blockIdx.x / p.tiles_per_frame, ty = (int)blockIdx.x % p.tiles_per_frame;
+    int n = tile_of(0) / p.tiles_per_frame, ty = tile_of(0) % p.tiles_per_frame;
     const int dn = (int)gridDim.x / p.tiles_per_frame, dty = (int)gridDim.x % p.tiles_per_frame;
     for (int k = 0; k < T; ++k) {
       const int y0 = ty * p.rows_per_tile;
@@ -213,8 +220,13 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
         if (++slot == S::NRING) { slot = 0; ++round; }
       }
-      n += dn; ty += dty;
-      if (ty >= p.tiles_per_frame) { ty -= p.tiles_per_frame; ++n; }
+      if (p.reverse) {
+        n -= dn; ty -= dty;
+        if (ty < 0) { ty += p.tiles_per_frame; --n; }
+      } else {
+        n += dn; ty += dty;
+        if (ty >= p.tiles_per_frame) { ty -= p.tiles_per_frame; ++n; }
+      }
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer: conv taps -> D1[group]
@@ -291,7 +303,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     uint8_t* e2buf = smem + S::OFF_E2 + grp * S::TAP_BYTES;
     mbar_wait(bar(S::W_FULL), 0);
     for (int k = grp; k < T; k += NG) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = tile_of(k);
       const uint32_t par = (uint32_t)(k / NG) & 1;
       // ---- epilogue 1: +bias, PReLU, bf16 -> e2 tile (A operand of the expansion) or global
       {
@@ -374,7 +386,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tma_store_commit();
         if constexpr (NARROW) {                       // every thread has read the residual tile: refill it
           if (k + NX < T) {
-            const int nt = blockIdx.x + (k + NX) * gridDim.x;
+            const int nt = tile_of(k + NX);
             mbar_expect_tx(bar(S::X_FULL + xb), S::RBUF);
             tma_load_2d(sbase + S::OFF_R + xb * S::RBUF, &map_x, 0, nt * 128, bar(S::X_FULL + xb));
             asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&xfills[xb])), "r"((uint32_t)((k + NX) / NX)) : "memory");
@@ -404,7 +416,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tma_store_wait_read();
         if constexpr (!NARROW) {
           if (k + NX < T) {
-            const int nt = blockIdx.x + (k + NX) * gridDim.x;
+            const int nt = tile_of(k + NX);
             mbar_expect_tx(bar(S::X_FULL + xb), S::XBUF);
             for (int s = 0; s < S::NSUB; ++s)
               tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb));
@@ -583,6 +595,12 @@ void umma_free(UmmaPack& p) {
   p = UmmaPack();
 }
 
+// Set by the scheduler (api.cu) before each launch: 1 = walk the tiles from the last to the first.  The
+// activations of a 256-frame batch (134-268 MB per tensor) do not fit the 126 MB L2, but the tail of what
+// a kernel wrote is still there when the next one starts: a consumer that walks in the opposite direction
+// reads those tiles first (measured: 3 % per launch).
+int g_umma_reverse = 0;
+
 template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
 static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
@@ -609,6 +627,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   for (int t = 0; t < ntaps; ++t) { p.dy[t] = taps.dy[t]; p.dx[t] = taps.dx[t]; }
   if ((conv_only != 0) != CONV) return cudaErrorInvalidValue;
   p.rowslab = rowslab ? 1 : 0;
+  p.reverse = g_umma_reverse;
   p.has_next = has_next;
   p.out_small = out_small;
   p.wblob = pk.wblob;
