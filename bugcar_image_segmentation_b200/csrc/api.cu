@@ -629,8 +629,9 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
   int H = 128, W = 256;   // resolution of X
   if (stop_after == -1) { launch_export_nchw<T>(X, dump, n, 16, H, W, s); return BC_OK; }
   int block_index = 0;
-  // direction in which the tensor now in X was written; a tcgen05 bottleneck launch walks the other way
-  // (kernels without a reverse walk run forward)
+  // direction in which the tensor now in X was written; the next kernel walks the other way.  Every kernel
+  // after the initial block can walk backwards; the CUDA-core fall-backs (fp32 mode, tensor cores off) ignore
+  // the flag, which only costs the L2 hits
   static const bool snake = getenv("BC_NO_SNAKE") == nullptr;
   int x_dir = 0;
   auto flip_dir = [&]() { x_dir = snake ? !x_dir : 0; g_umma_reverse = x_dir; };
@@ -656,11 +657,11 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           cudaError_t ce = cudaSuccess;
           L(c, b.cin == 16 ? "umma_pool_conv16" : "umma_pool_conv64", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + cip * esz),
             2.0 * px * 4 * b.cin * b.ci, s,
-            [&] { ce = launch_umma_down(b.um_b, (const bf16*)X, (bf16*)P, idx, (bf16*)E1, n, H, W, c->num_sms, s); });
+            [&] { flip_dir(); ce = launch_umma_down(b.um_b, (const bf16*)X, (bf16*)P, idx, (bf16*)E1, n, H, W, c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 pooling launch: ") + cudaGetErrorString(ce));
           L(c, b.cout == 64 ? "umma_down64" : "umma_down128", px * (cip + b.cin + b.cout + b.um_a.CN) * esz,
             2.0 * px * (9.0 * b.ci * b.ci + (double)b.ci * b.cout + (double)b.cout * b.um_a.CN), s,
-            [&] { x_dir = 0; flip_dir();      // the pooling kernel above wrote P / E1 front to back
+            [&] { flip_dir();                 // against the pooling kernel above, which wrote P / E1
                   ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)P, (bf16*)Y, (bf16*)E2, n, H, W, taps_for(3, 3, 1), 0, 1,
                                    c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 down-sampling launch: ") + cudaGetErrorString(ce));
@@ -709,7 +710,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
         // stage 5: K = 4 is too skinny for tcgen05; one fused CUDA-core kernel, x in, y out
         const double px = (double)n * H * W;
         L(c, "stage5_bottleneck", px * 2.0 * b.cin * esz, 2.0 * px * (16.0 * 4 + 9.0 * 16 + 4.0 * 16), s,
-          [&] { launch_stage5<T>(X, Y, b, n, H, W, s); });
+          [&] { flip_dir(); launch_stage5<T>(X, Y, b, n, H, W, s); });
         e1_ready = false;
         done = true;
       }
@@ -736,12 +737,12 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           const int has_next = b.um_a.has_next ? 1 : 0;
           L(c, b.cout == 64 ? "umma_up4" : "umma_up5", px * (b.cin * esz + b.cout + 4.0 * b.cout * esz + has_next * 4.0 * 16 * esz),
             2.0 * px * ((double)b.cin * (b.cout + b.ci) + 4.0 * b.ci * b.ci + 4.0 * b.ci * b.cout + has_next * 4.0 * 64 * 16), s,
-            [&] { ce = launch_umma_up(b.um_a, b.cin, b.cout, (const bf16*)X, idx, (bf16*)Y, (bf16*)E1, n, H, W, has_next,
+            [&] { flip_dir();
+                  ce = launch_umma_up(b.um_a, b.cin, b.cout, (const bf16*)X, idx, (bf16*)Y, (bf16*)E1, n, H, W, has_next,
                                       c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 upsampling launch: ") + cudaGetErrorString(ce));
           e1_ready = has_next != 0;
           done = true;
-          x_dir = 0;                    // the upsampling kernel walks front to back
         }
       }
       if (!done) {
@@ -760,7 +761,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
     if constexpr (std::is_same<T, bf16>::value) {
       cudaError_t ce = cudaSuccess;
       L(c, "umma_head_argmax_lut", n * (32768.0 * 16 * esz + 131072.0), n * 2.0 * 32768 * 64 * 64, s,
-        [&] { ce = launch_umma_head((const bf16*)X, n, c->num_classes, c->d_head_umma, labels, *lut, c->num_sms, s); });
+        [&] { flip_dir(); ce = launch_umma_head((const bf16*)X, n, c->num_classes, c->d_head_umma, labels, *lut, c->num_sms, s); });
       if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 head launch: ") + cudaGetErrorString(ce));
       return BC_OK;
     }

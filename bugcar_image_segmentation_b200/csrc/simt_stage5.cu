@@ -25,12 +25,16 @@ static constexpr int S5_HW = S5_TW + 2, S5_HH = S5_TH + 2;      // with halo
 
 template <typename T>
 __global__ void __launch_bounds__(128)
-k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ Stage5Params p, int H, int W) {
+k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ Stage5Params p, int H, int W,
+                    int reverse) {
   __shared__ float4 se1[S5_HH * S5_HW];        // e1 of the tile + halo, 4 channels per pixel
   const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * S5_TW, y0 = blockIdx.y * S5_TH;
-  const T* xf = x + (size_t)blockIdx.z * H * W * 16;
-  T* yf = y + (size_t)blockIdx.z * H * W * 16;
+  // reverse: blocks are dispatched in (x, y, z) order, so mirroring all three walks the batch back to front
+  const int bx = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x, by = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y,
+            bz = reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+  const int x0 = bx * S5_TW, y0 = by * S5_TH;
+  const T* xf = x + (size_t)bz * H * W * 16;
+  T* yf = y + (size_t)bz * H * W * 16;
 
   // ---- phase 1: projection 16 -> 4 on the halo tile
   for (int i = tid; i < S5_HH * S5_HW; i += 128) {
@@ -91,7 +95,7 @@ void launch_stage5(const T* x, T* y, const Bottleneck& b, int B, int H, int W, c
   Stage5Params p;
   memcpy(&p, b.s5.data(), sizeof p);
   dim3 grid((W + S5_TW - 1) / S5_TW, (H + S5_TH - 1) / S5_TH, B);
-  k_stage5_bottleneck<T><<<grid, 128, 0, s>>>(x, y, p, H, W);
+  k_stage5_bottleneck<T><<<grid, 128, 0, s>>>(x, y, p, H, W, g_umma_reverse);
 }
 template void launch_stage5<float>(const float*, float*, const Bottleneck&, int, int, int, cudaStream_t);
 template void launch_stage5<bf16>(const bf16*, bf16*, const Bottleneck&, int, int, int, cudaStream_t);

@@ -24,6 +24,7 @@ namespace bc {
 
 struct DownParams {
   int num_tiles;          // 128-output-pixel tiles
+  int reverse;            // 1: walk the tiles from the last to the first (L2 reuse between consecutive kernels, enet_umma.cu)
   int rows_per_tile;      // output rows per tile (128 / Wo, at least 1)
   bf16* pooled;           // [out px][CIN]
   uint8_t* idx;           // [out px][CIN] window position of the maximum
@@ -93,7 +94,7 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
 
   if (warp == 0) {
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       if (k >= 1) mbar_wait(bar(TAP_EMPTY), (k - 1) & 1);
       mbar_expect_tx_e(bar(TAP_FULL), 4 * S::TAP);
 #pragma unroll
@@ -121,7 +122,7 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
     const int m = q4 * 32 + lane;
     const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       const int b = k & 1;
       const size_t px = (size_t)tile * 128 + m;
       // ---- main branch: max-pool with argmax straight from the tap tiles
@@ -199,6 +200,7 @@ static cudaError_t down_launch_t(const UmmaPack& pk, const bf16* x, bf16* pooled
   if (!make_map_window(&mx, x, n, Ho, Wo, CIN, rows, box_w)) return cudaErrorInvalidValue;
   DownParams p{};
   p.num_tiles = n * Ho * Wo / 128;
+  p.reverse = g_umma_reverse;
   p.rows_per_tile = rows;
   p.pooled = pooled;
   p.idx = idx;

@@ -22,6 +22,7 @@ namespace bc {
 
 struct HeadParams {
   int num_tiles;            // B * 128 rows * 2 half-rows
+  int reverse;            // 1: walk the tiles from the last to the first (L2 reuse between consecutive kernels, enet_umma.cu)
   int C;                    // classes (<= 16)
   const uint8_t* wblob;     // [4 taps][64 rows = q*16+class][16 k] bf16, 32-byte swizzled rows
   uint8_t* labels;          // (B,256,512)
@@ -77,7 +78,7 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
 
   if (warp == 0) {
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       const int n = tile >> 8, y = (tile & 255) >> 1, x0 = (tile & 1) * 128;
       const int st = k % HEAD_STAGES;
       if (k >= HEAD_STAGES) mbar_wait(bar(TAP_EMPTY0 + st), ((k / HEAD_STAGES) - 1) & 1);
@@ -106,7 +107,7 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
     const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
     const int C = p.C;
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       const int n = tile >> 8, y = (tile & 255) >> 1, x = (tile & 1) * 128 + m;
       const int b = k & 1;
       mbar_wait(bar(D_FULL0 + b), (k >> 1) & 1);
@@ -171,6 +172,7 @@ cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, 
   if (!make_map_box(&mx, x, B, 128, 256, 16, 129, 1)) return cudaErrorInvalidValue;
   HeadParams p{};
   p.num_tiles = B * 256;
+  p.reverse = g_umma_reverse;
   p.C = C;
   p.wblob = wblob;
   p.labels = labels;

@@ -18,6 +18,7 @@ namespace bc {
 
 struct UpParams {
   int num_tiles;          // low-resolution 128-pixel tiles
+  int reverse;            // 1: walk the tiles from the last to the first (L2 reuse between consecutive kernels, enet_umma.cu)
   int tiles_per_frame;    // Hl * Wl / 128
   int Wl;                 // low-resolution width (64 or 128)
   int has_next;
@@ -112,7 +113,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
 
   if (warp == 0) {
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       const int b = k % S::NXB;
       if (k >= S::NXB) mbar_wait(bar(X_EMPTY0 + b), ((k / S::NXB) - 1) & 1);
       mbar_expect_tx_e(bar(X_FULL0 + b), S::XBUF);
@@ -174,7 +175,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
     const int lr = m / p.Wl, lx = m % p.Wl;             // position of my low-res pixel inside the tile
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
-      const int tile = blockIdx.x + k * gridDim.x;
+      const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       // ---- E_A: e1 = act(proj + b1) -> smem
       mbar_wait(bar(DA_FULL), k & 1);
       tc_fence_after();
@@ -359,6 +360,7 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
   else if (!make_map_rows(&my, y, lpx * 4, COUT, 256, 32)) return cudaErrorInvalidValue;
   UpParams p{};
   p.num_tiles = (int)(lpx / 128);
+  p.reverse = g_umma_reverse;
   p.tiles_per_frame = Hl * Wl / 128;
   p.Wl = Wl;
   p.has_next = has_next;
