@@ -156,6 +156,7 @@ struct bc_ctx {
   // ---- host entry point: copy stream for H2D / compute overlap
   int host_overlap = 1;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t d2h_stream = nullptr;       // grids of the streaming entry point leave on their own stream
   cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t call_start = nullptr;
 
@@ -1092,6 +1093,7 @@ void bc_destroy(bc_ctx* c) {
     for (cudaEvent_t e : {sl.copied, sl.computed, sl.done}) if (e) cudaEventDestroy(e);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   for (auto e : c->copy_done) if (e) cudaEventDestroy(e);
   if (c->call_start) cudaEventDestroy(c->call_start);
   void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out, c->cn_scratch,
@@ -1497,6 +1499,7 @@ int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B
     CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
   }
   if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!c->d2h_stream) CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   if (sl.in_bytes < in_bytes || sl.out_bytes < out_bytes) {
     CU(cudaDeviceSynchronize());
     invalidate_graphs(c);
@@ -1521,8 +1524,11 @@ int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B
   CU(cudaEventRecord(sl.copied, c->copy_stream));
   CU(cudaStreamWaitEvent(s, sl.copied, 0));
   if ((r = run_pipeline(c, sl.d_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, sl.d_out, s))) return r;
-  CU(cudaMemcpyAsync(h_grids, sl.d_out, out_bytes, cudaMemcpyDeviceToHost, s));
-  CU(cudaEventRecord(sl.done, s));
+  // the grids leave on a third stream, so the next step's kernels (already queued on `s`) start at once
+  CU(cudaEventRecord(sl.computed, s));
+  CU(cudaStreamWaitEvent(c->d2h_stream, sl.computed, 0));
+  CU(cudaMemcpyAsync(h_grids, sl.d_out, out_bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CU(cudaEventRecord(sl.done, c->d2h_stream));
   sl.busy = true;
   c->submitted++;
   return BC_OK;

@@ -181,7 +181,7 @@ int bc_pipeline_host(bc_ctx* ctx, const uint8_t* h_bgr, int h, int w, int B,
                      int binary, int ros_layout, int8_t* h_grids, void* stream);
 
 /* Streaming form for a driver loop that keeps the GPU busy: submit returns once the step is
- * enqueued (H2D on an internal copy stream, kernels + D2H on `stream`); two staging slots
+ * enqueued (H2D and D2H on internal copy streams, kernels on `stream`); two staging slots
  * alternate, so the copy of step i+1 overlaps the kernels of step i.  A third submit blocks until
  * the oldest step has finished.  bc_pipeline_host_wait(ctx, k) returns when at most k (0 or 1)
  * submitted steps are still in flight; the grids of finished steps are in their h_grids buffers,
