@@ -293,13 +293,22 @@ def main():
                 pipe.run_device(stage[j], d_grids)
                 computed[j].record(stream)
                 allg = sharding.gather_grids(d_grids, rank, world)
-            if rank == 0:
-                pinned_out2[j].copy_(allg, non_blocking=True)
-            done[j].record(stream)
+            if rank == 0:                                        # the grids leave on their own stream (two gather buffers)
+                gathered[j].record(stream)
+                d2h_stream.wait_event(gathered[j])
+                if peer is None:
+                    allg.record_stream(d2h_stream)                # a fresh tensor per step on the NCCL-gather path
+                with torch.cuda.stream(d2h_stream):
+                    pinned_out2[j].copy_(allg, non_blocking=True)
+                    done[j].record(d2h_stream)
+            else:
+                done[j].record(stream)
             done[j ^ 1].synchronize()                           # step i-1's grids are on the host
 
     if world > 1:
         copy_stream = torch.cuda.Stream()
+        d2h_stream = torch.cuda.Stream()
+        gathered = [torch.cuda.Event() for _ in range(2)]
         stage = [torch.empty_like(dev_sets[0]) for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
         computed = [torch.cuda.Event() for _ in range(2)]
@@ -338,7 +347,8 @@ def main():
     # ---- end to end through the host entry point
     for i in range(args.warmup):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps, finish=(lambda: model.ctx.pipeline_host_wait(0)) if world == 1 else None)
+    ms_e2e = timed(step_e2e, args.steps, finish=(lambda: model.ctx.pipeline_host_wait(0)) if world == 1 else
+                   (lambda: [e.synchronize() for e in done]))
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     step_e2e(0)                                          # untimed: grids of input set 0 for the CPU cross-check
