@@ -14,7 +14,9 @@ Deliberate deviations: no ``cv2.imshow`` inside the path (bev.py:132,213) and no
 ``print`` (bev.py:38,80,86); ``save_to_JSON`` also writes ``is_laserscan`` so that its
 output can be re-loaded (the reference's cannot, bev.py:47-55 vs bev.py:37);
 laserscan mode (bev.py:145-164, 216-240) reads uninitialised ``warpPolar`` memory in
-the reference and is not reproduced: it raises NotImplementedError.
+the reference (its output is not a function of its input); here those outlier pixels are
+0, i.e. the result equals the reference's with ``WARP_FILL_OUTLIERS`` set in its two
+``cv2.warpPolar`` calls (``bc_occgrid_laserscan``).
 """
 import json
 
