@@ -39,6 +39,7 @@ struct UmmaParams {
   int ntaps;
   int8_t dy[9], dx[9];
   int reverse;          // 1: walk the tiles from the last to the first (see launch_one: L2 reuse between consecutive kernels)
+  int vslab;            // 1: 5x1 conv on a full-width two-row tile: ONE 6-row box per tile, ky taps = descriptors 64 pixels apart
   int rowslab;          // 1: 3x3 dilation-1 conv on a one-row tile: 3 row loads of 130 pixels, kx through shifted descriptors
   int has_next;         // 1: compute the next block's projection from the y tile
   bf16* out_small;      // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
@@ -204,7 +205,14 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     const int dn = (int)gridDim.x / p.tiles_per_frame, dty = (int)gridDim.x % p.tiles_per_frame;
     for (int k = 0; k < T; ++k) {
       const int y0 = ty * p.rows_per_tile;
-      if (CI == 16 && p.rowslab) {
+      if (CI == 32 && p.vslab) {
+        // vertical taps of a full-width tile: rows y0-2 .. y0+3 arrive as one box (three ring slots), tap ky starts ky rows in
+        if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
+        mbar_expect_tx_e(bar(S::TAP_FULL + slot), 3 * S::TAP_BYTES);
+        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, 0, y0 - 2, n, bar(S::TAP_FULL + slot));
+        slot += 3;
+        if (slot == S::NRING) { slot = 0; ++round; }
+      } else if (CI == 16 && p.rowslab) {
         // one-row tiles: the three taps of a kernel row are the same 130-pixel row slab read at 0 / 1 / 2 pixels
         // offset (map_e1's box is 130 pixels wide here): 3 loads and a third of the L2 -> SM bytes per tile
         for (int ky = 0; ky < 3; ++ky) {
@@ -236,7 +244,19 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     for (int k = 0; k < T; ++k) {
       const int g = k % NG;
       if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
-      if (CI == 16 && p.rowslab) {
+      if (CI == 32 && p.vslab) {
+        mbar_wait(bar(S::TAP_FULL + slot), round & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)                    // one image row = 64 pixels x 64 bytes = 8 swizzle atoms
+#pragma unroll
+          for (int kk = 0; kk < CI / 16; ++kk)
+            umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + ky * 256 + kk * 2),
+                        dB0 + (uint64_t)(ky * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (ky | kk) != 0);
+        umma_commit_e(bar(S::TAP_EMPTY + slot));
+        slot += 3;
+        if (slot == S::NRING) { slot = 0; ++round; }
+      } else if (CI == 16 && p.rowslab) {
         for (int ky = 0; ky < 3; ++ky) {
           mbar_wait(bar(S::TAP_FULL + slot), round & 1);
           tc_fence_after();
@@ -609,7 +629,12 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   // row-slab mode: a plain 3x3 conv (dilation 1, taps in row-major order) whose 128-pixel tile is one image row
   bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && getenv("BC_NO_ROWSLAB") == nullptr;
   for (int t = 0; rowslab && t < 9; ++t) rowslab = taps.dy[t] == t / 3 - 1 && taps.dx[t] == t % 3 - 1;
-  if (rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1) : !make_map_e1(&me1, e1, n, H, W, CI)) return cudaErrorInvalidValue;
+  // vertical-slab mode: a 5x1 conv (taps dy = -2..2, dx = 0) whose tile is two full-width rows of 64 pixels
+  bool vslab = CI == 32 && S::NRING == 9 && ntaps == 5 && W == 64 && getenv("BC_NO_VSLAB") == nullptr;
+  for (int t = 0; vslab && t < 5; ++t) vslab = taps.dy[t] == t - 2 && taps.dx[t] == 0;
+  if (rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1)
+              : vslab ? !make_map_box(&me1, e1, n, H, W, CI, 64, 6) : !make_map_e1(&me1, e1, n, H, W, CI))
+    return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
   if (S::NARROW) {
     if (!make_map_rows(&mx, x, px, CRES, 128, S::RES_RB)) return cudaErrorInvalidValue;
@@ -627,6 +652,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   for (int t = 0; t < ntaps; ++t) { p.dy[t] = taps.dy[t]; p.dx[t] = taps.dx[t]; }
   if ((conv_only != 0) != CONV) return cudaErrorInvalidValue;
   p.rowslab = rowslab ? 1 : 0;
+  p.vslab = vslab ? 1 : 0;
   p.reverse = g_umma_reverse;
   p.has_next = has_next;
   p.out_small = out_small;
