@@ -88,6 +88,8 @@ def capture(rep, out_txt, header, stall_reps=()):
 
 
 traffic = {}
+if os.path.isfile(os.path.join(P, "traffic.json")):            # captures that were not re-taken keep their entries
+    traffic = json.load(open(os.path.join(P, "traffic.json")))
 traffic.update(capture(os.path.join(G, f"{rnd}_step_light.ncu-rep"), os.path.join(P, f"{rnd}_step_ncu.txt"),
                        "# ncu --section SpeedOfLight --section MemoryWorkloadAnalysis_Tables --section LaunchStats --section Occupancy "
                        "--section SchedulerStats --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum "
