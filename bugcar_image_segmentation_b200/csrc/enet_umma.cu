@@ -619,7 +619,7 @@ void umma_free(UmmaPack& p) {
 // activations of a 256-frame batch (134-268 MB per tensor) do not fit the 126 MB L2, but the tail of what
 // a kernel wrote is still there when the next one starts: a consumer that walks in the opposite direction
 // reads those tiles first (measured: 3 % per launch).
-int g_umma_reverse = 0;
+thread_local int g_umma_reverse = 0;     // one context per thread (include/bugcar_b200.h): no sharing
 
 template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
 static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H,

@@ -99,7 +99,7 @@ void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cud
 // ------------------------------------------------------------------ launchers (enet_umma.cu)
 // Fused bottleneck on tcgen05 (bf16 only): conv taps on e1 -> [expansion + residual -> y ->
 // next block's projection].  See enet_umma.cu for the data flow.
-extern int g_umma_reverse;                    // tile walk direction of the next launch_umma (see enet_umma.cu)
+extern thread_local int g_umma_reverse;                    // tile walk direction of the next launch_umma (see enet_umma.cu)
 bool umma_available();                        // driver exposes cuTensorMapEncodeTiled
 bool umma_supported(const Bottleneck& bn);    // regular / dilated / asymmetric at C = 64 or 128
 bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* conv_w, int ntaps, const float* conv_b,
