@@ -13,6 +13,7 @@
 #include "umma_common.cuh"
 
 #include <cstring>
+#include <type_traits>
 
 namespace bc {
 
@@ -49,6 +50,10 @@ struct UpSmem {
   // upsample5_0 (COUT = 16) is small enough for three CTAs per SM with one x buffer and D_c aliased
   // onto D_b (dead once epilogue B has read it); upsample4_0 fills the SM with one CTA
   static constexpr int MINB = COUT == 16 ? 3 : 1;
+  // upsample4_0 keeps ONE tile in flight per SM, so its four epilogues are the critical path: two warps per TMEM
+  // lane quarter, each taking half of the columns / taps / rows of every epilogue
+  static constexpr int EPW = COUT == 64 ? 2 : 1;
+  static constexpr int THREADS = 64 + 128 * EPW;
   static constexpr int NXB = COUT == 16 ? 1 : 2;       // x buffers
   static constexpr int OFF_X = 0;
   static constexpr int OFF_E1 = OFF_X + NXB * XBUF;
@@ -71,7 +76,7 @@ struct UpSmem {
 };
 
 template <int CIN, int CI, int COUT>
-__global__ void __launch_bounds__(192, (UpSmem<CIN, CI, COUT>::MINB))
+__global__ void __launch_bounds__((UpSmem<CIN, CI, COUT>::THREADS), (UpSmem<CIN, CI, COUT>::MINB))
 k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box [128][64], 128-byte swizzle
           const __grid_constant__ CUtensorMap map_y,   // 2D [high px][COUT], box = one staged row
           const __grid_constant__ UpParams p) {
@@ -94,7 +99,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
     const int one[] = {X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, DA_FULL, DB_FULL, DC_FULL, OUT_EMPTY, DD_FULL, W_FULL};
     for (int b : one) mbar_init(bar(b), 1);
     const int all[] = {E1_FULL, E2_FULL, OUT_FULL};
-    for (int b : all) mbar_init(bar(b), 128);
+    for (int b : all) mbar_init(bar(b), 128 * S::EPW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar(W_FULL), S::W_BYTES);
     bulk_load(sbase + S::OFF_W, p.wblob, S::W_BYTES, bar(W_FULL));
@@ -172,6 +177,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
     const int m = q4 * 32 + lane;
     const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
     const bool storer = (warp == 2 && lane == 0);
+    const int eh = (warp - 2) >> 2;                       // which half of every epilogue this warp takes (EPW == 2)
     const int lr = m / p.Wl, lx = m % p.Wl;             // position of my low-res pixel inside the tile
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
@@ -179,7 +185,22 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       // ---- E_A: e1 = act(proj + b1) -> smem
       mbar_wait(bar(DA_FULL), k & 1);
       tc_fence_after();
-      {
+      if constexpr (S::EPW == 2) {
+        static_assert(S::EPW == 1 || CI == 32, "split epilogue A assumes 32 internal channels");
+        auto ep_a = [&](auto H) {                       // compile-time half: the parameters stay constant-bank operands
+          constexpr int h = decltype(H)::value;
+          float v[16];
+          tmem_ld16(tm_lane + S::COL_A + COUT + 16 * h, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j] + p.f[F_B1 + 16 * h + j], p.f[F_A1 + 16 * h + j]);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            *reinterpret_cast<uint4*>(smem + S::OFF_E1 + swz<RB>(m * RB + (2 * h + c) * 16)) =
+                make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+        };
+        if (eh == 0) ep_a(std::integral_constant<int, 0>{}); else ep_a(std::integral_constant<int, 1>{});
+      } else {
         float v[CI];
         if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_A + COUT, v); else tmem_ld16(tm_lane + S::COL_A + COUT, v);
 #pragma unroll
@@ -197,7 +218,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       mbar_wait(bar(DB_FULL), k & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = 0; t < 4; ++t) {
+      for (int t = (S::EPW == 2 ? 2 * eh : 0); t < (S::EPW == 2 ? 2 * eh + 2 : 4); ++t) {
         float v[CI];
         if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_B + t * CI, v); else tmem_ld16(tm_lane + S::COL_B + t * CI, v);
 #pragma unroll
@@ -217,7 +238,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       tc_fence_after();
       const uint8_t* ip = p.idx + ((size_t)tile * 128 + m) * COUT;
 #pragma unroll(COUT == 64 ? 1 : 4)   // 64 channels: a rolled loop (dynamic constant-bank index) beats 4x the code
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
+      for (int c0 = (S::EPW == 2 ? eh * (COUT / 2) : 0); c0 < (S::EPW == 2 ? (eh + 1) * (COUT / 2) : COUT); c0 += 16) {
         float mainv[16];
         tmem_ld16(tm_lane + S::COL_A + c0, mainv);
         const uint4 iv = *reinterpret_cast<const uint4*>(ip + c0);
@@ -264,7 +285,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
           const int y0 = (tile % p.tiles_per_frame) * rows_lo;
           const size_t hrow0 = (size_t)n * (p.tiles_per_frame * rows_lo * 2) + 2 * y0;
 #pragma unroll 1
-          for (int r = 0; r < 4; ++r) {
+          for (int r = (S::EPW == 2 ? 2 * eh : 0); r < (S::EPW == 2 ? 2 * eh + 2 : 4); ++r) {
             float v[16];
             tmem_ld16(tm_lane + S::COL_D + r * 16, v);
 #pragma unroll
@@ -378,7 +399,7 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
   static_assert((S::TOTAL + 2048) * S::MINB <= 233472 && S::TMEM_COLS * S::MINB <= 512, "CTAs per SM");
   const int ctas = num_sms * S::MINB;                    // upsample5_0 fits three times per SM: three tiles in flight
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  k_umma_up<CIN, CI, COUT><<<grid, 192, smem, s>>>(mx, my, p);
+  k_umma_up<CIN, CI, COUT><<<grid, S::THREADS, smem, s>>>(mx, my, p);
   return cudaGetLastError();
 }
 
