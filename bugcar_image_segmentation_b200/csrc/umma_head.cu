@@ -40,6 +40,9 @@ static constexpr int HEAD_OFF_BAR = HEAD_OFF_LUT + 256;
 static constexpr int HEAD_SMEM = HEAD_OFF_BAR + 128;
 
 // 44 KB of shared memory and 128 TMEM columns per CTA: four CTAs per SM keep four tiles in flight
+// CT: the class count as a compile-time constant (0 = read it from the parameters): the argmax loop then carries
+// no per-class range predicate
+template <int CT>
 __global__ void __launch_bounds__(192, 4)
 k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][129][16], 32-byte swizzle
             const HeadParams p) {
@@ -105,7 +108,7 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
     const int q4 = warp & 3;
     const int m = q4 * 32 + lane;
     const uint32_t tm_lane = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int C = p.C;
+    const int C = CT ? CT : p.C;
     for (int k = 0; k < T; ++k) {
       const int tile = p.reverse ? p.num_tiles - 1 - ((int)blockIdx.x + k * (int)gridDim.x) : (int)blockIdx.x + k * (int)gridDim.x;
       const int n = tile >> 8, y = (tile & 255) >> 1, x = (tile & 1) * 128 + m;
@@ -180,12 +183,16 @@ cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, 
   static bool attr_done = false;
   const int smem = HEAD_SMEM + 1024;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_head, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_umma_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   int grid = p.num_tiles < 4 * num_sms ? p.num_tiles : 4 * num_sms;
-  k_umma_head<<<grid, 192, smem, s>>>(mx, p);
+  if (C == 15) k_umma_head<15><<<grid, 192, smem, s>>>(mx, p);          // note_label:1-15
+  else if (C == 16) k_umma_head<16><<<grid, 192, smem, s>>>(mx, p);
+  else k_umma_head<0><<<grid, 192, smem, s>>>(mx, p);
   return cudaGetLastError();
 }
 
