@@ -83,8 +83,8 @@ def test_edges(cn):
 
 
 def test_full_batch_properties(cn):
-    """bs 256 at network resolution: the batched launch equals per-frame launches, the filter is
-    idempotent on its own output when nothing was XOR-ed out, and output is always {0,1}."""
+    """bs 256 at network resolution: the batched launch equals per-frame launches (frame i and its copy
+    at i + 240 agree, and both agree with a single-frame call), and the output is always {0,1}."""
     import torch
     from bugcar_image_segmentation_b200 import synth
     base = np.stack([synth.road_mask(2000 + i) for i in range(16)])
