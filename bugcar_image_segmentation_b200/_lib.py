@@ -12,7 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libbugcar_b200.so")
 
 BC_OK, BC_ERR_ARG, BC_ERR_STATE, BC_ERR_CUDA, BC_ERR_FORMAT, BC_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 BC_IN_BGR_U8, BC_IN_NCHW_F32, BC_IN_NCHW_F64 = 0, 1, 2
-BC_PREC_BF16, BC_PREC_FP32 = 0, 1
+BC_PREC_BF16, BC_PREC_FP32, BC_PREC_FP16 = 0, 1, 2
+PRECISIONS = {"fp16": BC_PREC_FP16, "float16": BC_PREC_FP16, "half": BC_PREC_FP16, "bf16": BC_PREC_BF16,
+              "bfloat16": BC_PREC_BF16, "fp32": BC_PREC_FP32, "float32": BC_PREC_FP32}
 NET_H, NET_W = 256, 512          # models.py:19
 
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t

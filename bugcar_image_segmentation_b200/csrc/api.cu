@@ -11,6 +11,7 @@
 #include "internal.h"
 #include "../../include/bugcar_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -66,7 +67,13 @@ struct ProfRec {
   cudaEvent_t start, stop;
 };
 
-inline float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// value of a weight as the 16-bit kernels of `precision` read it (fp32 mode: unchanged)
+inline float round_to(int precision, float v) {
+  if (precision == BC_PREC_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (precision == BC_PREC_FP16) return __half2float(__float2half_rn(std::min(std::max(v, -65504.f), 65504.f)));
+  return v;
+}
+template <typename T> struct is16 { static constexpr bool value = std::is_same<T, bf16>::value || std::is_same<T, f16>::value; };
 
 }  // namespace
 
@@ -78,7 +85,7 @@ struct bc_ctx {
   std::string err;
   long long launches = 0;
 
-  int precision = BC_PREC_BF16;
+  int precision = BC_PREC_FP16;
   int chunk = 0;            // 0 = default
   int tensor_cores = 1;
   bool umma_ready = false;
@@ -169,6 +176,24 @@ struct bc_ctx {
 
 static std::string g_create_err;
 
+namespace bc {
+// Set by the scheduler (forward_chunk) before each tcgen05 launch: 1 = walk the tiles from the last to the
+// first.  The activations of a 256-frame batch (134-268 MB per tensor) do not fit the 126 MB L2, but the tail
+// of what a kernel wrote is still there when the next one starts: a consumer that walks in the opposite
+// direction reads those tiles first (measured: 3 % per launch).
+thread_local int g_umma_reverse = 0;     // one context per thread (include/bugcar_b200.h): no sharing
+
+bool umma_supported(const Bottleneck& bn) {
+  if (bn.kind != 1 && bn.kind != 2) return false;
+  return (bn.cin == 128 && bn.ci == 32) || (bn.cin == 64 && bn.ci == 16);
+}
+
+void umma_free(UmmaPack& p) {
+  if (p.wblob) cudaFree(p.wblob);
+  p = UmmaPack();
+}
+}  // namespace bc
+
 namespace {
 
 int fail(bc_ctx* c, int code, const std::string& msg) {
@@ -238,9 +263,17 @@ int parse_container(bc_ctx* c, const void* blob, size_t n, Container& out) {
     if (ndim > 4) return fail(c, BC_ERR_FORMAT, std::string(name) + ": ndim > 4");
     Tensor t;
     t.ndim = (int)ndim;
-    for (int k = 0; k < 4; ++k) t.dims[k] = (int)d[k];
-    size_t cnt = t.count();
-    if (data0 + off + cnt * 4 > n) return fail(c, BC_ERR_FORMAT, std::string(name) + ": data out of bounds");
+    size_t cnt = 1;
+    for (int k = 0; k < 4; ++k) {
+      t.dims[k] = (int)d[k];
+      if (k >= (int)ndim) continue;
+      // no ENet tensor has an axis beyond a few hundred: a cap keeps the product far from overflow
+      if (d[k] < 1 || d[k] > 65536) return fail(c, BC_ERR_FORMAT, std::string(name) + ": dimension outside [1, 65536]");
+      cnt *= d[k];
+      if (cnt > (size_t)1 << 32) return fail(c, BC_ERR_FORMAT, std::string(name) + ": tensor too large");
+    }
+    const size_t avail = n - data0;
+    if (off > avail || cnt * 4 > avail - off) return fail(c, BC_ERR_FORMAT, std::string(name) + ": data out of bounds");
     if ((data0 + off) % 4 != 0) return fail(c, BC_ERR_FORMAT, std::string(name) + ": misaligned data");
     t.data = (const float*)(p + data0 + off);
     out.t[name] = t;
@@ -423,12 +456,12 @@ void free_net(bc_ctx* c) {
   c->d_init_w = c->d_init_g = c->d_init_b = c->d_init_a = c->d_full_w = nullptr;
 }
 
-int upload_vec(bc_ctx* c, const std::vector<float>& v, bool round_bf16, float** out) {
+int upload_vec(bc_ctx* c, const std::vector<float>& v, bool round16, float** out) {
   std::vector<float> tmp;
   const float* src = v.data();
-  if (round_bf16) {
+  if (round16 && c->precision != BC_PREC_FP32) {
     tmp.resize(v.size());
-    for (size_t i = 0; i < v.size(); ++i) tmp[i] = bf16_round(v[i]);
+    for (size_t i = 0; i < v.size(); ++i) tmp[i] = round_to(c->precision, v[i]);
     src = tmp.data();
   }
   float* d = nullptr;
@@ -454,42 +487,11 @@ void invalidate_graphs(bc_ctx* c) {
   c->graphs.clear();
 }
 
-int upload_net(bc_ctx* c) {
-  invalidate_graphs(c);
-  free_net(c);
-  const bool bf = c->precision == BC_PREC_BF16;
-  int r;
-  // The initial block and the head read fp32 weights in both modes, except that bf16 mode
-  // rounds the head's weights (its input is bf16 and the oracle's emulation does the same).
-  if ((r = upload_vec(c, c->h_init_w, false, &c->d_init_w))) return r;
-  if ((r = upload_vec(c, c->h_init_g, false, &c->d_init_g))) return r;
-  if ((r = upload_vec(c, c->h_init_b, false, &c->d_init_b))) return r;
-  if ((r = upload_vec(c, c->h_init_a, false, &c->d_init_a))) return r;
-  if ((r = upload_vec(c, c->h_full_w, bf, &c->d_full_w))) return r;
-  for (const HostBlock& hb : c->h_blocks) {
-    Bottleneck b;
-    b.name = hb.name; b.kind = hb.kind; b.cin = hb.cin; b.cout = hb.cout; b.ci = hb.ci; b.dilation = hb.dilation;
-    if ((r = upload_conv(c, hb.c1, bf, b.c1))) return r;
-    if ((r = upload_conv(c, hb.c2, bf, b.c2))) return r;
-    if ((r = upload_conv(c, hb.c2b, bf, b.c2b))) return r;
-    if ((r = upload_conv(c, hb.c3, bf, b.c3))) return r;
-    if ((r = upload_conv(c, hb.cm, bf, b.cm))) return r;
-    if ((r = upload_vec(c, hb.alpha_out, false, &b.alpha_out))) return r;
-    if (hb.kind == 1 && hb.cin == 16 && hb.ci == 4) {      // stage 5: parameters travel by value (simt_stage5.cu)
-      Stage5Params sp;
-      auto wv = [&](float v) { return bf ? bf16_round(v) : v; };      // same operand rounding as upload_conv
-      for (int i = 0; i < 64; ++i) { sp.w1[i] = wv(hb.c1.w[i]); sp.w3[i] = wv(hb.c3.w[i]); }
-      for (int i = 0; i < 144; ++i) sp.w2[i] = wv(hb.c2.w[i]);
-      for (int i = 0; i < 4; ++i) { sp.b1[i] = hb.c1.bias[i]; sp.a1[i] = hb.c1.alpha[i]; sp.b2[i] = hb.c2.bias[i]; sp.a2[i] = hb.c2.alpha[i]; }
-      for (int i = 0; i < 16; ++i) { sp.b3[i] = hb.c3.bias[i]; sp.a3[i] = hb.c3.alpha[i]; sp.aout[i] = hb.alpha_out[i]; }
-      b.s5.resize(sizeof sp / sizeof(float));
-      memcpy(b.s5.data(), &sp, sizeof sp);
-    }
-    c->blocks.push_back(b);
-  }
-  // tcgen05 operand packs (bf16 mode): conv (+ expansion + the NEXT block's projection)
-  c->umma_ready = false;
-  if (bf && umma_available()) {
+// tcgen05 operand packs (16-bit modes): conv (+ expansion + the NEXT block's projection)
+template <typename AT>
+int build_umma_packs(bc_ctx* c) {
+  typedef Umma<AT> U;
+  if (U::available()) {
     for (size_t i = 0; i < c->blocks.size(); ++i) {
       Bottleneck& b = c->blocks[i];
       if (b.kind == 3) {     // upsampling bottleneck (+ the next regular block's projection when it is 64 wide)
@@ -497,7 +499,7 @@ int upload_net(bc_ctx* c) {
         const HostBlock* nx = nullptr;
         if (b.cout == 64 && i + 1 < c->blocks.size() && umma_supported(c->blocks[i + 1]) && c->blocks[i + 1].cin == 64)
           nx = &c->h_blocks[i + 1];
-        if (!up_build(b.um_a, b.cin, b.ci, b.cout, hb.cm.w.data(), hb.cm.bias.data(), hb.c1.w.data(), hb.c1.bias.data(),
+        if (!U::up_build(b.um_a, b.cin, b.ci, b.cout, hb.cm.w.data(), hb.cm.bias.data(), hb.c1.w.data(), hb.c1.bias.data(),
                       hb.c1.alpha.data(), hb.c2.w.data(), hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
                       hb.c3.bias.data(), hb.alpha_out.data(), nx ? nx->c1.w.data() : nullptr,
                       nx ? nx->c1.bias.data() : nullptr, nx ? nx->c1.alpha.data() : nullptr))
@@ -516,10 +518,10 @@ int upload_net(bc_ctx* c) {
         for (int o = 0; o < b.ci; ++o) { cb[o] = hb.c2.bias[o]; ca[o] = hb.c2.alpha[o]; }
         for (int k = 0; k < b.ci; ++k)
           for (int o = 0; o < b.cout; ++o) ew[(size_t)k * b.cout + o] = hb.c3.w[(size_t)k * b.cout + o];
-        if (!umma_build(b.um_a, b.cout, cip, nx.ci, b.cin, cw.data(), 9, cb.data(), ca.data(), ew.data(), hb.c3.bias.data(),
+        if (!U::build(b.um_a, b.cout, cip, nx.ci, b.cin, cw.data(), 9, cb.data(), ca.data(), ew.data(), hb.c3.bias.data(),
                         hb.c3.alpha.data(), hb.alpha_out.data(), nx.c1.w.data(), nx.c1.bias.data(), nx.c1.alpha.data()))
           return fail(c, BC_ERR_CUDA, "building the tcgen05 down-sampling operands failed");
-        if (!down_build(b.um_b, b.cin, b.ci, hb.c1.w.data(), hb.c1.bias.data(), hb.c1.alpha.data()))
+        if (!U::down_build(b.um_b, b.cin, b.ci, hb.c1.w.data(), hb.c1.bias.data(), hb.c1.alpha.data()))
           return fail(c, BC_ERR_CUDA, "building the tcgen05 pooling / strided-conv operands failed");
         continue;
       }
@@ -533,26 +535,65 @@ int upload_net(bc_ctx* c) {
       const float* na = nx ? nx->c1.alpha.data() : nullptr;
       bool ok;
       if (b.kind == 1) {
-        ok = umma_build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 9, hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
+        ok = U::build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 9, hb.c2.bias.data(), hb.c2.alpha.data(), hb.c3.w.data(),
                         hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
       } else {
-        ok = umma_build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 5, hb.c2.bias.data(), hb.c2.alpha.data(), nullptr, nullptr,
+        ok = U::build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 5, hb.c2.bias.data(), hb.c2.alpha.data(), nullptr, nullptr,
                         nullptr, nullptr, nullptr, nullptr, nullptr) &&
-             umma_build(b.um_b, b.cin, b.ci, b.ci, b.cin, hb.c2b.w.data(), 5, hb.c2b.bias.data(), hb.c2b.alpha.data(), hb.c3.w.data(),
+             U::build(b.um_b, b.cin, b.ci, b.ci, b.cin, hb.c2b.w.data(), 5, hb.c2b.bias.data(), hb.c2b.alpha.data(), hb.c3.w.data(),
                         hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
     }
-    if (!initial_build(&c->d_init_umma, c->h_init_w.data()) || !initial_build_u8(&c->d_init_umma_u8, c->h_init_w.data()))
+    if (!U::initial_build(&c->d_init_umma, c->h_init_w.data()) || !U::initial_build_u8(&c->d_init_umma_u8, c->h_init_w.data()))
       return fail(c, BC_ERR_CUDA, "building the tcgen05 initial-block operands failed");
     if (c->num_classes <= 16) {
       std::vector<float> hw(c->h_full_w.size());
-      for (size_t i = 0; i < hw.size(); ++i) hw[i] = bf16_round(c->h_full_w[i]);
-      if (!head_build(&c->d_head_umma, hw.data(), c->num_classes, 16))
+      for (size_t i = 0; i < hw.size(); ++i) hw[i] = round_to(c->precision, c->h_full_w[i]);
+      if (!U::head_build(&c->d_head_umma, hw.data(), c->num_classes, 16))
         return fail(c, BC_ERR_CUDA, "building the tcgen05 head operands failed");
     }
     c->umma_ready = true;
   }
+  return BC_OK;
+}
+
+int upload_net(bc_ctx* c) {
+  invalidate_graphs(c);
+  free_net(c);
+  const bool bf = c->precision != BC_PREC_FP32;     // 16-bit storage: operands rounded to that type
+  int r;
+  // The initial block and the head read fp32 weights in every mode, except that the 16-bit modes
+  // round the head's weights (its input is 16-bit and the oracle's emulation does the same).
+  if ((r = upload_vec(c, c->h_init_w, false, &c->d_init_w))) return r;
+  if ((r = upload_vec(c, c->h_init_g, false, &c->d_init_g))) return r;
+  if ((r = upload_vec(c, c->h_init_b, false, &c->d_init_b))) return r;
+  if ((r = upload_vec(c, c->h_init_a, false, &c->d_init_a))) return r;
+  if ((r = upload_vec(c, c->h_full_w, bf, &c->d_full_w))) return r;
+  for (const HostBlock& hb : c->h_blocks) {
+    Bottleneck b;
+    b.name = hb.name; b.kind = hb.kind; b.cin = hb.cin; b.cout = hb.cout; b.ci = hb.ci; b.dilation = hb.dilation;
+    if ((r = upload_conv(c, hb.c1, bf, b.c1))) return r;
+    if ((r = upload_conv(c, hb.c2, bf, b.c2))) return r;
+    if ((r = upload_conv(c, hb.c2b, bf, b.c2b))) return r;
+    if ((r = upload_conv(c, hb.c3, bf, b.c3))) return r;
+    if ((r = upload_conv(c, hb.cm, bf, b.cm))) return r;
+    if ((r = upload_vec(c, hb.alpha_out, false, &b.alpha_out))) return r;
+    if (hb.kind == 1 && hb.cin == 16 && hb.ci == 4) {      // stage 5: parameters travel by value (simt_stage5.cu)
+      Stage5Params sp;
+      auto wv = [&](float v) { return round_to(c->precision, v); };   // same operand rounding as upload_conv
+      for (int i = 0; i < 64; ++i) { sp.w1[i] = wv(hb.c1.w[i]); sp.w3[i] = wv(hb.c3.w[i]); }
+      for (int i = 0; i < 144; ++i) sp.w2[i] = wv(hb.c2.w[i]);
+      for (int i = 0; i < 4; ++i) { sp.b1[i] = hb.c1.bias[i]; sp.a1[i] = hb.c1.alpha[i]; sp.b2[i] = hb.c2.bias[i]; sp.a2[i] = hb.c2.alpha[i]; }
+      for (int i = 0; i < 16; ++i) { sp.b3[i] = hb.c3.bias[i]; sp.a3[i] = hb.c3.alpha[i]; sp.aout[i] = hb.alpha_out[i]; }
+      b.s5.resize(sizeof sp / sizeof(float));
+      memcpy(b.s5.data(), &sp, sizeof sp);
+    }
+    c->blocks.push_back(b);
+  }
+  c->umma_ready = false;
+  if (c->precision == BC_PREC_BF16) return build_umma_packs<bf16>(c);
+  if (c->precision == BC_PREC_FP16) return build_umma_packs<f16>(c);
   return BC_OK;
 }
 
@@ -572,7 +613,7 @@ int chunk_frames(const bc_ctx* c) {
 
 int ensure_scratch(bc_ctx* c) {
   int frames = chunk_frames(c);
-  int esz = c->precision == BC_PREC_BF16 ? 2 : 4;
+  int esz = c->precision == BC_PREC_FP32 ? 4 : 2;
   if (c->scratch_frames == frames && c->scratch_esz == esz) return BC_OK;
   invalidate_graphs(c);
   free_scratch(c);
@@ -612,12 +653,12 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
   const double esz = sizeof(T);
   const double in_px_bytes = kind == BC_IN_BGR_U8 ? 3.0 : kind == BC_IN_NCHW_F32 ? 12.0 : 24.0;
   bool init_tc = false;
-  if constexpr (std::is_same<T, bf16>::value) init_tc = c->tensor_cores && c->umma_ready && c->d_init_umma;
+  if constexpr (is16<T>::value) init_tc = c->tensor_cores && c->umma_ready && c->d_init_umma;
   if (init_tc) {
-    if constexpr (std::is_same<T, bf16>::value) {
+    if constexpr (is16<T>::value) {
       cudaError_t ce = cudaSuccess;
       L(c, "umma_initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
-        ce = launch_umma_initial(x, kind, n, (bf16*)X, c->d_init_umma, c->d_init_umma_u8, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
+        ce = Umma<T>::launch_initial(x, kind, n, X, c->d_init_umma, c->d_init_umma_u8, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
                                  c->h_init_a.data(), c->num_sms, s);
       });
       if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 initial-block launch: ") + cudaGetErrorString(ce));
@@ -651,20 +692,19 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       uint8_t* idx = b.cin == 16 ? c->idx1 : c->idx2;
       double px = (double)n * H * W;
       bool tc = false;
-      if constexpr (std::is_same<T, bf16>::value) tc = c->tensor_cores && c->umma_ready && b.um_a.wblob != nullptr;
+      if constexpr (is16<T>::value) tc = c->tensor_cores && c->umma_ready && b.um_a.wblob != nullptr;
       const int cip = tc ? b.um_a.CI : b.ci;       // e1 width as stored (zero-padded to 16 for tcgen05)
       if (tc) {
-        if constexpr (std::is_same<T, bf16>::value) {
+        if constexpr (is16<T>::value) {
           cudaError_t ce = cudaSuccess;
           L(c, b.cin == 16 ? "umma_pool_conv16" : "umma_pool_conv64", px * (4.0 * b.cin * esz + b.cin * esz + b.cin + cip * esz),
             2.0 * px * 4 * b.cin * b.ci, s,
-            [&] { flip_dir(); ce = launch_umma_down(b.um_b, (const bf16*)X, (bf16*)P, idx, (bf16*)E1, n, H, W, c->num_sms, s); });
+            [&] { flip_dir(); ce = Umma<T>::launch_down(b.um_b, X, P, idx, E1, n, H, W, c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 pooling launch: ") + cudaGetErrorString(ce));
           L(c, b.cout == 64 ? "umma_down64" : "umma_down128", px * (cip + b.cin + b.cout + b.um_a.CN) * esz,
             2.0 * px * (9.0 * b.ci * b.ci + (double)b.ci * b.cout + (double)b.cout * b.um_a.CN), s,
             [&] { flip_dir();                 // against the pooling kernel above, which wrote P / E1
-                  ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)P, (bf16*)Y, (bf16*)E2, n, H, W, taps_for(3, 3, 1), 0, 1,
-                                   c->num_sms, s); });
+                  ce = Umma<T>::launch(b.um_a, E1, P, Y, E2, n, H, W, taps_for(3, 3, 1), 0, 1, c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 down-sampling launch: ") + cudaGetErrorString(ce));
           std::swap(E1, E2);          // e1' of the next block was written to E2
           e1_ready = true;
@@ -679,8 +719,8 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       std::swap(X, Y);
     } else if (b.kind == 1 || b.kind == 2) {
       bool done = false;
-      if (c->tensor_cores && c->umma_ready && c->precision == BC_PREC_BF16 && umma_supported(b)) {
-        if constexpr (std::is_same<T, bf16>::value) {
+      if (c->tensor_cores && c->umma_ready && umma_supported(b)) {
+        if constexpr (is16<T>::value) {
           const double px = (double)n * H * W;
           if (!e1_ready) conv("proj1x1", X, E1, nullptr, 0, b.c1, nullptr, t1);
           cudaError_t ce = cudaSuccess;
@@ -690,17 +730,14 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
           if (b.kind == 1) {
             L(c, b.cin == 64 ? "umma_bottleneck64" : "umma_bottleneck128", io,
               2.0 * px * (9.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
-              [&] { ce = launch_umma(b.um_a, (const bf16*)E1, (const bf16*)X, (bf16*)Y, (bf16*)E2, n, H, W,
-                                     taps_for(3, 3, b.dilation), 0, has_next, c->num_sms, s); });
+              [&] { ce = Umma<T>::launch(b.um_a, E1, X, Y, E2, n, H, W, taps_for(3, 3, b.dilation), 0, has_next, c->num_sms, s); });
             std::swap(E1, E2);        // e1' of the next block was written to E2
           } else {
             L(c, "umma_conv5x1", px * 2.0 * b.ci * esz, 2.0 * px * 5.0 * b.ci * b.ci, s,
-              [&] { ce = launch_umma(b.um_a, (const bf16*)E1, nullptr, nullptr, (bf16*)E2, n, H, W, taps_for(5, 1, 1), 1, 0,
-                                     c->num_sms, s); });
+              [&] { ce = Umma<T>::launch(b.um_a, E1, nullptr, nullptr, E2, n, H, W, taps_for(5, 1, 1), 1, 0, c->num_sms, s); });
             if (ce == cudaSuccess)
               L(c, "umma_bottleneck128_asym", io, 2.0 * px * (5.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
-                [&] { ce = launch_umma(b.um_b, (const bf16*)E2, (const bf16*)X, (bf16*)Y, (bf16*)E1, n, H, W,
-                                       taps_for(1, 5, 1), 0, has_next, c->num_sms, s); });
+                [&] { ce = Umma<T>::launch(b.um_b, E2, X, Y, E1, n, H, W, taps_for(1, 5, 1), 0, has_next, c->num_sms, s); });
           }
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 bottleneck launch: ") + cudaGetErrorString(ce));
           e1_ready = has_next != 0;
@@ -733,14 +770,13 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
       double px = (double)n * H * W;
       bool done = false;
       if (c->tensor_cores && c->umma_ready && b.um_a.wblob) {
-        if constexpr (std::is_same<T, bf16>::value) {
+        if constexpr (is16<T>::value) {
           cudaError_t ce = cudaSuccess;
           const int has_next = b.um_a.has_next ? 1 : 0;
           L(c, b.cout == 64 ? "umma_up4" : "umma_up5", px * (b.cin * esz + b.cout + 4.0 * b.cout * esz + has_next * 4.0 * 16 * esz),
             2.0 * px * ((double)b.cin * (b.cout + b.ci) + 4.0 * b.ci * b.ci + 4.0 * b.ci * b.cout + has_next * 4.0 * 64 * 16), s,
             [&] { flip_dir();
-                  ce = launch_umma_up(b.um_a, b.cin, b.cout, (const bf16*)X, idx, (bf16*)Y, (bf16*)E1, n, H, W, has_next,
-                                      c->num_sms, s); });
+                  ce = Umma<T>::launch_up(b.um_a, b.cin, b.cout, X, idx, Y, E1, n, H, W, has_next, c->num_sms, s); });
           if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 upsampling launch: ") + cudaGetErrorString(ce));
           e1_ready = has_next != 0;
           done = true;
@@ -759,10 +795,10 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
     if (block_index++ == stop_after) { launch_export_nchw<T>(X, dump, n, b.cout, H, W, s); return BC_OK; }
   }
   if (labels && c->tensor_cores && c->umma_ready && c->d_head_umma) {
-    if constexpr (std::is_same<T, bf16>::value) {
+    if constexpr (is16<T>::value) {
       cudaError_t ce = cudaSuccess;
       L(c, "umma_head_argmax_lut", n * (32768.0 * 16 * esz + 131072.0), n * 2.0 * 32768 * 64 * 64, s,
-        [&] { flip_dir(); ce = launch_umma_head((const bf16*)X, n, c->num_classes, c->d_head_umma, labels, *lut, c->num_sms, s); });
+        [&] { flip_dir(); ce = Umma<T>::launch_head(X, n, c->num_classes, c->d_head_umma, labels, *lut, c->num_sms, s); });
       if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 head launch: ") + cudaGetErrorString(ce));
       return BC_OK;
     }
@@ -794,7 +830,8 @@ int forward(bc_ctx* c, const void* x, int kind, int B, float* logits, uint8_t* l
     const void* xi = (const uint8_t*)x + fb * f0;
     float* lo = logits ? logits + (size_t)f0 * c->num_classes * px : nullptr;
     uint8_t* la = labels ? labels + (size_t)f0 * px : nullptr;
-    if (c->precision == BC_PREC_BF16) r = forward_chunk<bf16>(c, xi, kind, n, lo, la, lut, s);
+    if (c->precision == BC_PREC_FP16) r = forward_chunk<f16>(c, xi, kind, n, lo, la, lut, s);
+    else if (c->precision == BC_PREC_BF16) r = forward_chunk<bf16>(c, xi, kind, n, lo, la, lut, s);
     else r = forward_chunk<float>(c, xi, kind, n, lo, la, lut, s);
     if (r) return r;
   }
@@ -917,7 +954,13 @@ int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int 
   launch_occ_table(key, d, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { cudaFree(d); return fail(c, BC_ERR_CUDA, std::string("occupancy table: ") + cudaGetErrorString(e)); }
-  if (c->occ_tables.size() >= 8) { cudaFree(c->occ_tables.front().second); c->occ_tables.erase(c->occ_tables.begin()); }
+  if (c->occ_tables.size() >= 8) {
+    // cached graphs hold the evicted table's address (GraphKey does not): drop them with it.  The synchronise
+    // above covered every kernel that could still read the table.
+    invalidate_graphs(c);
+    cudaFree(c->occ_tables.front().second);
+    c->occ_tables.erase(c->occ_tables.begin());
+  }
   c->occ_tables.emplace_back(key, d);
   g.table = d;
   return BC_OK;
@@ -932,7 +975,13 @@ int8_t* grid_dest(bc_ctx* c, int8_t* d_grids, int B, const BevGeom& g) {
 int ensure_contour_scratch(bc_ctx* c, int B, int H, int W) {
   size_t need = contour_scratch_bytes(B, H, W);
   if (need <= c->cn_scratch_bytes) return BC_OK;
-  if (c->cn_scratch) { cudaFree(c->cn_scratch); c->cn_scratch = nullptr; c->cn_scratch_bytes = 0; }
+  if (c->cn_scratch) {
+    // pipeline graphs captured with the contour filter on hold the old scratch address
+    cudaDeviceSynchronize();
+    invalidate_graphs(c);
+    cudaFree(c->cn_scratch);
+    c->cn_scratch = nullptr; c->cn_scratch_bytes = 0;
+  }
   if (cudaMalloc(&c->cn_scratch, need) != cudaSuccess) {
     cudaGetLastError();
     return fail(c, BC_ERR_NOMEM, "contour_noise_removal scratch: out of device memory");
@@ -1052,11 +1101,29 @@ int bc_create(bc_ctx** out, int device, int max_batch) {
   if (prop.major != 10)
     return fail(c, BC_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 (Blackwell B200); this library carries sm_100a code only");
   if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(c, BC_ERR_CUDA, cudaGetErrorString(e));
-  std::unique_ptr<bc_ctx> ctx(new bc_ctx());
+  std::unique_ptr<bc_ctx, void (*)(bc_ctx*)> ctx(new bc_ctx(), bc_destroy);   // a failed create releases what it made
   c = ctx.get();
   c->device = device;
   c->max_batch = max_batch;
   c->num_sms = prop.multiProcessorCount;
+  // kernels that need more than 48 KB of dynamic shared memory: the opt-in is a per-device function
+  // attribute, so every context sets it for its own GPU (one process may hold contexts on several GPUs)
+  CU(prepare_occgrid());
+  CU(Umma<bf16>::prepare_bottleneck()); CU(Umma<f16>::prepare_bottleneck());
+  CU(Umma<bf16>::prepare_initial());    CU(Umma<f16>::prepare_initial());
+  CU(Umma<bf16>::prepare_down());       CU(Umma<f16>::prepare_down());
+  CU(Umma<bf16>::prepare_up());         CU(Umma<f16>::prepare_up());
+  CU(Umma<bf16>::prepare_head());       CU(Umma<f16>::prepare_head());
+  // streams and events of the host entry points
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  for (auto& e : c->copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->call_start, cudaEventDisableTiming));
+  for (auto& sl : c->slots) {
+    CU(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
   // normalisation LUT, fp64 exactly as numpy evaluates (rgb / 256.0 - mean) / std (models.py:91)
   const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18
   std::vector<double> l64(768);
@@ -1121,13 +1188,17 @@ int bc_num_classes(const bc_ctx* c) { return (c && c->net_loaded) ? c->num_class
 
 int bc_set_precision(bc_ctx* c, int precision) {
   if (!c) return BC_ERR_ARG;
-  if (precision != BC_PREC_BF16 && precision != BC_PREC_FP32) return fail(c, BC_ERR_ARG, "unknown precision");
+  if (precision != BC_PREC_BF16 && precision != BC_PREC_FP32 && precision != BC_PREC_FP16)
+    return fail(c, BC_ERR_ARG, "unknown precision");
   if (precision == c->precision) return BC_OK;
   c->precision = precision;
   if (c->net_loaded) {
     CU(cudaSetDevice(c->device));
     CU(cudaDeviceSynchronize());
-    return upload_net(c);
+    c->net_loaded = false;          // a failed upload leaves no half-built network behind
+    int r = upload_net(c);
+    if (r) return r;
+    c->net_loaded = true;
   }
   return BC_OK;
 }
@@ -1238,7 +1309,8 @@ int bc_enet_block_output(bc_ctx* c, const void* d_x, int kind, int B, int block,
   int r;
   if ((r = ensure_scratch(c))) return r;
   if (B < 1 || B > c->scratch_frames) return fail(c, BC_ERR_ARG, "batch size outside [1, chunk]");
-  if (c->precision == BC_PREC_BF16) r = forward_chunk<bf16>(c, d_x, kind, B, nullptr, nullptr, nullptr, (cudaStream_t)stream, block, d_out);
+  if (c->precision == BC_PREC_FP16) r = forward_chunk<f16>(c, d_x, kind, B, nullptr, nullptr, nullptr, (cudaStream_t)stream, block, d_out);
+  else if (c->precision == BC_PREC_BF16) r = forward_chunk<bf16>(c, d_x, kind, B, nullptr, nullptr, nullptr, (cudaStream_t)stream, block, d_out);
   else r = forward_chunk<float>(c, d_x, kind, B, nullptr, nullptr, nullptr, (cudaStream_t)stream, block, d_out);
   if (r) return r;
   return check_launch(c, "block output");
@@ -1442,11 +1514,6 @@ int bc_pipeline_host(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const
     CU(cudaStreamSynchronize(s));
     return BC_OK;
   }
-  if (!c->copy_stream) {
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (auto& e : c->copy_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->call_start, cudaEventDisableTiming));
-  }
   // the copy stream must not overwrite the staging buffer while earlier work on `s` may still read it
   CU(cudaEventRecord(c->call_start, s));
   CU(cudaStreamWaitEvent(c->copy_stream, c->call_start, 0));
@@ -1493,13 +1560,6 @@ int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B
   bc_ctx::Slot& sl = c->slots[c->submitted & 1];
   const size_t in_bytes = (size_t)B * h * w * 3, out_bytes = (size_t)B * g.Hc * g.Wc;
   if (sl.busy) { CU(cudaEventSynchronize(sl.done)); sl.busy = false; }      // at most two steps in flight
-  if (!sl.copied) {
-    CU(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
-  }
-  if (!c->copy_stream) CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  if (!c->d2h_stream) CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   if (sl.in_bytes < in_bytes || sl.out_bytes < out_bytes) {
     CU(cudaDeviceSynchronize());
     invalidate_graphs(c);

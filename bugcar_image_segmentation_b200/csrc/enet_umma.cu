@@ -1,5 +1,5 @@
-// ENet bottlenecks on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), bf16 storage,
-// fp32 accumulation.  One kernel per bottleneck:
+// ENet bottlenecks on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), 16-bit storage
+// (fp16 or bf16, see umma_common.cuh), fp32 accumulation.  One kernel per bottleneck:
 //
 //   e1 (CI ch, produced by the previous kernel) --TMA tap boxes--> smem
 //        conv KxK / dilated / 5x1 / 1x5  : NT taps x (CI/16) tcgen05.mma   -> D1 [128 x CI]  (TMEM)
@@ -30,6 +30,7 @@
 #include <mutex>
 
 namespace bc {
+namespace BC_NS {
 
 // =================================================================== the kernel
 struct UmmaParams {
@@ -42,7 +43,7 @@ struct UmmaParams {
   int vslab;            // 1: 5x1 conv on a full-width two-row tile: ONE 6-row box per tile, ky taps = descriptors 64 pixels apart
   int rowslab;          // 1: 3x3 dilation-1 conv on a one-row tile: 3 row loads of 130 pixels, kx through shifted descriptors
   int has_next;         // 1: compute the next block's projection from the y tile
-  bf16* out_small;      // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
+  act_t* out_small;     // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
   const uint8_t* wblob; // packed weights, exact shared-memory image (see UmmaSmem)
   // fp32 bias / PReLU-slope block b2[CI] a2[CI] b3[C] a3[C] aout[C] b1n[CN] a1n[CN], by value: the
   // epilogues index it with compile-time channel numbers, so every use is a constant-bank operand
@@ -251,7 +252,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         for (int ky = 0; ky < 5; ++ky)                    // one image row = 64 pixels x 64 bytes = 8 swizzle atoms
 #pragma unroll
           for (int kk = 0; kk < CI / 16; ++kk)
-            umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + ky * 256 + kk * 2),
+            umma_mma_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + ky * 256 + kk * 2),
                         dB0 + (uint64_t)(ky * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (ky | kk) != 0);
         umma_commit_e(bar(S::TAP_EMPTY + slot));
         slot += 3;
@@ -262,7 +263,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           tc_fence_after();
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)                  // the swizzle follows the absolute address: a 32-byte shift is legal
-            umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + kx * 2),
+            umma_mma_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + kx * 2),
                         dB0 + (uint64_t)((ky * 3 + kx) * (Wt::W2_TAP >> 4)), IDESC_CONV, (ky | kx) != 0);
           umma_commit_e(bar(S::TAP_EMPTY + slot));
           if (++slot == S::NRING) { slot = 0; ++round; }
@@ -273,7 +274,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_bf16_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + kk * 2),
+          umma_mma_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + kk * 2),
                       dB0 + (uint64_t)(t * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (t | kk) != 0);
         umma_commit_e(bar(S::TAP_EMPTY + slot));          // slot reusable once these MMAs retire
         if (++slot == S::NRING) { slot = 0; ++round; }
@@ -291,7 +292,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_bf16_e(tmem + S::COL_D2 + g * C, dA0 + (uint64_t)(g * (S::TAP_BYTES >> 4) + kk * 2), dB0 + (uint64_t)(kk * 2),
+          umma_mma_e(tmem + S::COL_D2 + g * C, dA0 + (uint64_t)(g * (S::TAP_BYTES >> 4) + kk * 2), dB0 + (uint64_t)(kk * 2),
                       IDESC_EXP, kk != 0);
         umma_commit_e(bar(S::D2_FULL + g));
       }
@@ -308,7 +309,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < C / 16; ++kk)
-          umma_bf16_e(tmem + S::COL_D3 + g * CN, dA0 + (uint64_t)(xo + (kk / 4) * (S::XSUB >> 4) + (kk % 4) * 2),
+          umma_mma_e(tmem + S::COL_D3 + g * CN, dA0 + (uint64_t)(xo + (kk / 4) * (S::XSUB >> 4) + (kk % 4) * 2),
                       dB0 + (uint64_t)((kk / 4) * (Wt::W1_SUB >> 4) + (kk % 4) * 2), IDESC_PROJ, kk != 0);
         umma_commit_e(bar(S::D3_FULL + g));
       }
@@ -339,15 +340,12 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
 #pragma unroll
           for (int c = 0; c < CI / 8; ++c)
-            o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                              pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+            o[c] = pack8(v + 8 * c);
           continue;
         }
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
-          *reinterpret_cast<uint4*>(e2buf + swz<RB>(m * RB + c * 16)) =
-              make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                         pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+          *reinterpret_cast<uint4*>(e2buf + swz<RB>(m * RB + c * 16)) = pack8(v + 8 * c);
         fence_proxy_async();
         mbar_arrive(bar(S::E2_FULL + grp));
       }
@@ -382,17 +380,17 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           uint4 xr = make_uint4(0u, 0u, 0u, 0u);      // channels beyond CRES: zero padding of the main branch
           if constexpr (!NARROW) xr = *py;
           else if (ch < CRES) xr = *reinterpret_cast<const uint4*>(rt + swz<S::RES_RB>(m * S::RES_RB + (ch / 8) * 16));
-          const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr);
+          const uint32_t* xh = reinterpret_cast<const uint32_t*>(&xr);
           float o[8];
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
-            float2 xf = __bfloat1622float2(xh[qq]);
+            float2 xf = unpack_act(xh[qq]);
             int j = 8 * c + 2 * qq;
             o[2 * qq] = prelu_f(prelu_f(v[j] + p.f[F_B3 + c0 + j], p.f[F_A3 + c0 + j]) + xf.x, p.f[F_AOUT + c0 + j]);
             o[2 * qq + 1] = prelu_f(prelu_f(v[j + 1] + p.f[F_B3 + c0 + j + 1], p.f[F_A3 + c0 + j + 1]) + xf.y,
                                     p.f[F_AOUT + c0 + j + 1]);
           }
-          *py = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          *py = pack8(o);
         }
       }
       fence_proxy_async();
@@ -425,8 +423,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CN);
 #pragma unroll
         for (int c = 0; c < CN / 8; ++c)
-          o[c] = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                            pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+          o[c] = pack8(v + 8 * c);
       }
       // The y buffer may be overwritten once the store has read it (and the projection MMAs, which
       // the D3_FULL wait above covers, have consumed it).  In place: the thread that knows first
@@ -480,7 +477,7 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 // 4D map over a [N][H][W][CI] bf16 tensor; box = [1][rows][cols][CI] (128 pixels)
-bool make_map_e1(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI) {
+bool make_map_e1(CUtensorMap* m, const act_t* base, int N, int H, int W, int CI) {
   PFN_encodeTiled enc = encode_fn();
   if (!enc) return false;
   int rows = 128 / W > 0 ? 128 / W : 1;
@@ -488,74 +485,66 @@ bool make_map_e1(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI) 
   cuuint64_t strides[3] = {(cuuint64_t)CI * 2, (cuuint64_t)W * CI * 2, (cuuint64_t)H * W * CI * 2};
   cuuint32_t box[4] = {(cuuint32_t)CI, (cuuint32_t)(128 / rows), (cuuint32_t)rows, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, ACT_TMAP, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle_for(CI * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // same tensor view, explicit box [1][box_rows][box_w][CI]
-bool make_map_box(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI, int box_w, int box_rows) {
+bool make_map_box(CUtensorMap* m, const act_t* base, int N, int H, int W, int CI, int box_w, int box_rows) {
   PFN_encodeTiled enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[4] = {(cuuint64_t)CI, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)CI * 2, (cuuint64_t)W * CI * 2, (cuuint64_t)H * W * CI * 2};
   cuuint32_t box[4] = {(cuuint32_t)CI, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, ACT_TMAP, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle_for(CI * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // 2D map over [pixels][C] bf16; box = [128 px][64 ch], 128-byte swizzle
-bool make_map_x(CUtensorMap* m, const bf16* base, size_t pixels, int C) {
+bool make_map_x(CUtensorMap* m, const act_t* base, size_t pixels, int C) {
   PFN_encodeTiled enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
   cuuint64_t strides[1] = {(cuuint64_t)C * 2};
   cuuint32_t box[2] = {64, 128};
   cuuint32_t es[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, ACT_TMAP, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // 2D map over [pixels][C] bf16; box = [box_px][C] (whole pixel rows), swizzle = C * 2 bytes
-bool make_map_rows(CUtensorMap* m, const bf16* base, size_t pixels, int C, int box_px, int sw) {
+bool make_map_rows(CUtensorMap* m, const act_t* base, size_t pixels, int C, int box_px, int sw) {
   PFN_encodeTiled enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)pixels};
   cuuint64_t strides[1] = {(cuuint64_t)C * 2};
   cuuint32_t box[2] = {(cuuint32_t)C, (cuuint32_t)box_px};
   cuuint32_t es[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, ACT_TMAP, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle_for(sw), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // 5D window view of a [N][2Ho][2Wo][C] bf16 tensor: dims (C, dx, ox, dy, n*Ho + oy); one box =
 // one window position of `rows` output rows x `box_w` output pixels
-bool make_map_window(CUtensorMap* m, const bf16* base, int N, int Ho, int Wo, int C, int rows, int box_w) {
+bool make_map_window(CUtensorMap* m, const act_t* base, int N, int Ho, int Wo, int C, int rows, int box_w) {
   PFN_encodeTiled enc = encode_fn();
   if (!enc) return false;
   cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)Wo, 2, (cuuint64_t)N * Ho};
   cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * Wo * C * 2, (cuuint64_t)4 * Wo * C * 2};
   cuuint32_t box[5] = {(cuuint32_t)C, 1, (cuuint32_t)box_w, 1, (cuuint32_t)rows};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, ACT_TMAP, 5, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle_for(C * 2 >= 128 ? 128 : C * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool umma_available() { return encode_fn() != nullptr; }
-
-bool umma_supported(const Bottleneck& bn) {
-  if (bn.kind != 1 && bn.kind != 2) return false;
-  return (bn.cin == 128 && bn.ci == 32) || (bn.cin == 64 && bn.ci == 16);
-}
-
-// K-major operand image: rows of `row_bytes` (one swizzle row each), bf16, swizzled
+// K-major operand image: rows of `row_bytes` (one swizzle row each), 16-bit activation type, swizzled
 static void pack_rows(uint8_t* dst, int rows, int row_bytes, const std::vector<float>& w, int cin_total, int cout_total,
                       int tap, int k0) {
   // element (row = out channel o, k = in channel k0 + kk) of folded [tap][cin][cout]
   int kper = row_bytes / 2;
   for (int o = 0; o < rows; ++o)
     for (int kk = 0; kk < kper; ++kk) {
-      float v = w[((size_t)tap * cin_total + (k0 + kk)) * cout_total + o];
-      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const uint16_t h = host_act_bits(w[((size_t)tap * cin_total + (k0 + kk)) * cout_total + o]);
       uint32_t off = (uint32_t)(o * row_bytes + kk * 2);
       uint32_t so = row_bytes == 128 ? swz<128>(off) : row_bytes == 64 ? swz<64>(off) : swz<32>(off);
       memcpy(dst + so, &h, 2);
@@ -594,43 +583,17 @@ static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* 
   return true;
 }
 
-// (C, CI, CN, CRES) combinations of the ENet graph: regular stage-2/3 and stage-1/4 bottlenecks,
-// downsample1_0 (internal width 4 zero-padded to 16) and downsample2_0
-bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* conv_w, int ntaps, const float* conv_b,
-                const float* conv_a, const float* exp_w, const float* exp_b, const float* exp_a, const float* alpha_out,
-                const float* next_w, const float* next_b, const float* next_a) {
-  bool ok = false;
-  if (C == 128 && CI == 32 && CN == 32 && CRES == 128)
-    ok = build_t<128, 32, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
-  else if (C == 64 && CI == 16 && CN == 16 && (CRES == 64 || CRES == 16))
-    ok = build_t<64, 16, 16>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
-  else if (C == 128 && CI == 16 && CN == 32 && CRES == 64)
-    ok = build_t<128, 16, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
-  out.CRES = CRES;
-  return ok;
-}
-
-void umma_free(UmmaPack& p) {
-  if (p.wblob) cudaFree(p.wblob);
-  p = UmmaPack();
-}
-
-// Set by the scheduler (api.cu) before each launch: 1 = walk the tiles from the last to the first.  The
-// activations of a 256-frame batch (134-268 MB per tensor) do not fit the 126 MB L2, but the tail of what
-// a kernel wrote is still there when the next one starts: a consumer that walks in the opposite direction
-// reads those tiles first (measured: 3 % per launch).
-thread_local int g_umma_reverse = 0;     // one context per thread (include/bugcar_b200.h): no sharing
-
 template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
-static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H,
+static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
   using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
   CUtensorMap me1, mx, my;
   // row-slab mode: a plain 3x3 conv (dilation 1, taps in row-major order) whose 128-pixel tile is one image row
-  bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && getenv("BC_NO_ROWSLAB") == nullptr;
+  static const bool no_rowslab = getenv("BC_NO_ROWSLAB") != nullptr, no_vslab = getenv("BC_NO_VSLAB") != nullptr;   // read once
+  bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && !no_rowslab;
   for (int t = 0; rowslab && t < 9; ++t) rowslab = taps.dy[t] == t / 3 - 1 && taps.dx[t] == t % 3 - 1;
   // vertical-slab mode: a 5x1 conv (taps dy = -2..2, dx = 0) whose tile is two full-width rows of 64 pixels
-  bool vslab = CI == 32 && S::NRING == 9 && ntaps == 5 && W == 64 && getenv("BC_NO_VSLAB") == nullptr;
+  bool vslab = CI == 32 && S::NRING == 9 && ntaps == 5 && W == 64 && !no_vslab;
   for (int t = 0; vslab && t < 5; ++t) vslab = taps.dy[t] == t - 2 && taps.dx[t] == 0;
   if (rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1)
               : vslab ? !make_map_box(&me1, e1, n, H, W, CI, 64, 6) : !make_map_e1(&me1, e1, n, H, W, CI))
@@ -658,14 +621,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const bf16* e1, const bf16* x,
   p.out_small = out_small;
   p.wblob = pk.wblob;
   memcpy(p.f, pk.hf.data(), pk.hf.size() * sizeof(float));
-  static bool attr_done = false;
-  const int smem = S::TOTAL + 1024;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  const int smem = S::TOTAL + 1024;        // opt-in set per device by prepare_bottleneck()
   const int ctas = num_sms * MINB;
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
@@ -679,8 +635,45 @@ static int cfg_from_env(const char* name, int dflt) {
   return (v && v[0] >= '1' && v[0] <= '4' && v[1] >= '1' && v[1] <= '2' && !v[2]) ? (v[0] - '0') * 10 + (v[1] - '0') : dflt;
 }
 
-cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n, int H, int W,
-                        const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
+}  // namespace BC_NS
+using namespace BC_NS;
+
+bool Umma<act_t>::available() { return encode_fn() != nullptr; }
+
+// the kernel configurations launch() can select (one opt-in per instantiation and device)
+#define BC_UMMA_CONFIGS(X) \
+  X(128, 32, 32, 128, 2, 2, true) X(128, 32, 32, 128, 2, 1, false) X(64, 16, 16, 64, 1, 2, false) \
+  X(64, 16, 16, 64, 2, 2, false) X(64, 16, 16, 64, 4, 1, false) X(64, 16, 16, 16, 2, 2, false) X(128, 16, 32, 64, 2, 1, false)
+
+cudaError_t Umma<act_t>::prepare_bottleneck() {
+  cudaError_t e = cudaSuccess;
+#define BC_SET(C_, CI_, CN_, CR_, NG_, MB_, CV_)                                                              \
+  if (e == cudaSuccess)                                                                                        \
+    e = cudaFuncSetAttribute(k_umma_bottleneck<C_, CI_, CN_, CR_, NG_, MB_, CV_>,                              \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<C_, CI_, CN_, CR_, NG_, MB_, CV_>::TOTAL + 1024);
+  BC_UMMA_CONFIGS(BC_SET)
+#undef BC_SET
+  return e;
+}
+
+// (C, CI, CN, CRES) combinations of the ENet graph: regular stage-2/3 and stage-1/4 bottlenecks,
+// downsample1_0 (internal width 4 zero-padded to 16) and downsample2_0
+bool Umma<act_t>::build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* conv_w, int ntaps, const float* conv_b,
+                const float* conv_a, const float* exp_w, const float* exp_b, const float* exp_a, const float* alpha_out,
+                const float* next_w, const float* next_b, const float* next_a) {
+  bool ok = false;
+  if (C == 128 && CI == 32 && CN == 32 && CRES == 128)
+    ok = build_t<128, 32, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
+  else if (C == 64 && CI == 16 && CN == 16 && (CRES == 64 || CRES == 16))
+    ok = build_t<64, 16, 16>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
+  else if (C == 128 && CI == 16 && CN == 32 && CRES == 64)
+    ok = build_t<128, 16, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
+  out.CRES = CRES;
+  return ok;
+}
+
+cudaError_t Umma<act_t>::launch(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,
+                                int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
   if (128 % W != 0 && W % 128 != 0) return cudaErrorInvalidValue;
   static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 41);
 #define BC_LAUNCH(C_, CI_, CN_, CR_, NG_, MB_) \

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -11,6 +12,7 @@
 namespace bc {
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // ------------------------------------------------------------------ packed layers
 // One convolution (+ folded batch norm + activation slope) for the CUDA-core kernels.
@@ -96,43 +98,21 @@ void launch_stage5(const T* x, T* y, const Bottleneck& b, int B, int H, int W, c
 template <typename T>
 void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cudaStream_t s);
 
-// ------------------------------------------------------------------ launchers (enet_umma.cu)
-// Fused bottleneck on tcgen05 (bf16 only): conv taps on e1 -> [expansion + residual -> y ->
-// next block's projection].  See enet_umma.cu for the data flow.
-extern thread_local int g_umma_reverse;                    // tile walk direction of the next launch_umma (see enet_umma.cu)
-bool umma_available();                        // driver exposes cuTensorMapEncodeTiled
+// ------------------------------------------------------------------ tcgen05 kernels (enet_umma.cu, umma_*.cu)
+// Those sources are compiled once per 16-bit activation type (bf16: BC_PREC_BF16, fp16: BC_PREC_FP16;
+// see umma_common.cuh); Umma<AT> is the per-type set of entry points, declared in umma_api.inc.
+extern thread_local int g_umma_reverse;                    // tile walk direction of the next tcgen05 launch (api.cu)
 bool umma_supported(const Bottleneck& bn);    // regular / dilated / asymmetric at C = 64 or 128
-bool umma_build(UmmaPack& out, int C, int CI, int CN, int CRES, const float* conv_w, int ntaps, const float* conv_b,
-                const float* conv_a, const float* exp_w, const float* exp_b, const float* exp_a,
-                const float* alpha_out, const float* next_w, const float* next_b, const float* next_a);
 void umma_free(UmmaPack& p);
-cudaError_t launch_umma(const UmmaPack& pk, const bf16* e1, const bf16* x, bf16* y, bf16* out_small, int n,
-                        int H, int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s);
-
-// Initial block on tcgen05 (umma_initial.cu): 3xTF32 implicit GEMM + max-pool + BN + PReLU
-bool initial_build(uint8_t** out, const float* w);        // fp32 / fp64 NCHW inputs: 3xTF32
-bool initial_build_u8(uint8_t** out, const float* w);     // uint8 BGR frames: raw bytes + validity columns, bf16 limbs
-cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const uint8_t* wblob_u8,
-                                const float* lut, const float* g, const float* b, const float* a, int num_sms,
-                                cudaStream_t s);
-
-// First half of a down-sampling bottleneck on tcgen05 (umma_down.cu): max-pool + argmax and the
-// strided 2x2 conv from the same TMA-staged window tiles; e1 is written 16 wide (zero padded)
-bool down_build(UmmaPack& out, int cin, int ci, const float* w, const float* bias, const float* alpha);
-cudaError_t launch_umma_down(const UmmaPack& pk, const bf16* x, bf16* pooled, uint8_t* idx, bf16* e1, int n, int Ho, int Wo,
-                             int num_sms, cudaStream_t s);
-
-// Upsampling bottleneck on tcgen05 (umma_up.cu)
-bool up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const float* bm, const float* w1, const float* b1,
-              const float* a1, const float* wt, const float* bt, const float* at, const float* w3, const float* b3,
-              const float* aout, const float* w1n, const float* b1n, const float* a1n);
-cudaError_t launch_umma_up(const UmmaPack& pk, int cin, int cout, const bf16* x, const uint8_t* idx, bf16* y, bf16* e1_next,
-                           int n, int Hl, int Wl, int has_next, int num_sms, cudaStream_t s);
-
-// Head on tcgen05 (umma_head.cu): transposed conv 16 -> C (C <= 16) + argmax + LUT -> labels
-bool head_build(uint8_t** out, const float* w, int C, int CP);
-cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,
-                             int num_sms, cudaStream_t s);
+template <typename AT> struct Umma;
+template <> struct Umma<bf16> {
+  typedef bf16 AT;
+#include "umma_api.inc"
+};
+template <> struct Umma<f16> {
+  typedef f16 AT;
+#include "umma_api.inc"
+};
 
 // ------------------------------------------------------------------ launchers (prepost.cu)
 struct ResizeTab {          // device tables for cv2.resize INTER_LINEAR, one (h,w)
@@ -150,6 +130,7 @@ void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lu
                        uint8_t* labels, cudaStream_t s);
 void launch_occ_table(const BevGeom& g, uint4* table, cudaStream_t s);     // [25][Hc*Wc] entries, once per geometry
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s);   // needs g.table
+cudaError_t prepare_occgrid();            // dynamic shared-memory opt-in of K9 on the current device
 
 
 // ------------------------------------------------------------------ launchers (contour.cu)

@@ -307,13 +307,13 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
   }
 }
 
+static constexpr int OCC_SMEM = 25 * 128 * (int)sizeof(uint4);   // 51 200 B
+
+// the > 48 KB opt-in is per device: bc_create calls this for its GPU
+cudaError_t prepare_occgrid() { return cudaFuncSetAttribute(k_occgrid, cudaFuncAttributeMaxDynamicSharedMemorySize, OCC_SMEM); }
+
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s) {
-  static bool attr_done = false;
-  const int smem = 25 * 128 * (int)sizeof(uint4);   // 51 200 B
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_occgrid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_done = true;
-  }
+  const int smem = OCC_SMEM;
   dim3 grid((g.Hc * g.Wc + 127) / 128, (B + OCC_FRAMES - 1) / OCC_FRAMES);
   k_occgrid<<<grid, 128, smem, s>>>(labels, g, B, grids);
 }

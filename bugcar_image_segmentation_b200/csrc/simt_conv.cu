@@ -112,5 +112,6 @@ void launch_conv(const T* in, T* out, const T* res, int res_ch, const ConvP& c,
 }
 template void launch_conv<float>(const float*, float*, const float*, int, const ConvP&, const float*, int, int, int, const Taps&, cudaStream_t);
 template void launch_conv<bf16>(const bf16*, bf16*, const bf16*, int, const ConvP&, const float*, int, int, int, const Taps&, cudaStream_t);
+template void launch_conv<f16>(const f16*, f16*, const f16*, int, const ConvP&, const float*, int, int, int, const Taps&, cudaStream_t);
 
 }  // namespace bc

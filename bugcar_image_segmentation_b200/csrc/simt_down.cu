@@ -79,5 +79,6 @@ void launch_down_a(const T* x, int B, int H, int W, int cin, int ci, T* pooled, 
 }
 template void launch_down_a<float>(const float*, int, int, int, int, int, float*, uint8_t*, float*, const ConvP&, cudaStream_t);
 template void launch_down_a<bf16>(const bf16*, int, int, int, int, int, bf16*, uint8_t*, bf16*, const ConvP&, cudaStream_t);
+template void launch_down_a<f16>(const f16*, int, int, int, int, int, f16*, uint8_t*, f16*, const ConvP&, cudaStream_t);
 
 }  // namespace bc

@@ -116,5 +116,6 @@ void launch_fullconv(const T* x, int B, int C, const float* w, float* logits, ui
 }
 template void launch_fullconv<float>(const float*, int, int, const float*, float*, uint8_t*, const Lut256*, cudaStream_t);
 template void launch_fullconv<bf16>(const bf16*, int, int, const float*, float*, uint8_t*, const Lut256*, cudaStream_t);
+template void launch_fullconv<f16>(const f16*, int, int, const float*, float*, uint8_t*, const Lut256*, cudaStream_t);
 
 }  // namespace bc

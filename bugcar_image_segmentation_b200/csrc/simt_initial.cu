@@ -91,6 +91,7 @@ void launch_initial(const void* x, int kind, int B, T* out, const float* w, cons
 }
 template void launch_initial<float>(const void*, int, int, float*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
 template void launch_initial<bf16>(const void*, int, int, bf16*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
+template void launch_initial<f16>(const void*, int, int, f16*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
 
 // ------------------------------------------------------------- debug / parity export
 // NHWC activation (storage type T) -> fp32 NCHW, for per-block parity tests.
@@ -109,5 +110,6 @@ void launch_export_nchw(const T* in, float* out, int B, int C, int H, int W, cud
 }
 template void launch_export_nchw<float>(const float*, float*, int, int, int, int, cudaStream_t);
 template void launch_export_nchw<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
+template void launch_export_nchw<f16>(const f16*, float*, int, int, int, int, cudaStream_t);
 
 }  // namespace bc

@@ -99,5 +99,6 @@ void launch_stage5(const T* x, T* y, const Bottleneck& b, int B, int H, int W, c
 }
 template void launch_stage5<float>(const float*, float*, const Bottleneck&, int, int, int, cudaStream_t);
 template void launch_stage5<bf16>(const bf16*, bf16*, const Bottleneck&, int, int, int, cudaStream_t);
+template void launch_stage5<f16>(const f16*, f16*, const Bottleneck&, int, int, int, cudaStream_t);
 
 }  // namespace bc

@@ -119,5 +119,6 @@ void launch_up_b(const T* x, const T* e1, const uint8_t* idx, T* out, const Bott
 }
 template void launch_up_b<float>(const float*, const float*, const uint8_t*, float*, const Bottleneck&, int, int, int, cudaStream_t);
 template void launch_up_b<bf16>(const bf16*, const bf16*, const uint8_t*, bf16*, const Bottleneck&, int, int, int, cudaStream_t);
+template void launch_up_b<f16>(const f16*, const f16*, const uint8_t*, f16*, const Bottleneck&, int, int, int, cudaStream_t);
 
 }  // namespace bc

@@ -1,9 +1,26 @@
 // Device helpers shared by the tcgen05 kernels: mbarrier, TMA (tensor + bulk), tcgen05
 // MMA / commit / TMEM load, shared-memory and instruction descriptors, swizzle.
+//
+// The translation units that include this header are compiled TWICE (Makefile): with
+// -DBC_ACT_F16=0 the 16-bit activation / operand type is bf16 (namespace bc::as_bf16), with
+// -DBC_ACT_F16=1 it is IEEE fp16 (namespace bc::as_f16; same bytes, same TMA boxes, same
+// tcgen05.mma.kind::f16 with another format field, 8x less rounding error).  Everything that
+// depends on the type lives in namespace bc::BC_NS; the entry points are the members of
+// Umma<act_t> (internal.h).
 #pragma once
 #include "internal.h"
 
 #include <cuda.h>
+#include <cstring>
+
+#ifndef BC_ACT_F16
+#define BC_ACT_F16 0
+#endif
+#if BC_ACT_F16
+#define BC_NS as_f16
+#else
+#define BC_NS as_bf16
+#endif
 
 namespace bc {
 
@@ -78,8 +95,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (fp16 or bf16 operands per the instruction descriptor) -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -126,7 +143,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // every uniform-datapath instruction (UTCHMMA, UTCBAR, UTMALDG) in an ELECT / BRA.U.ANY loop and
 // recomputes its operands per lane; a service thread is on the critical path of every tile, so
 // its instruction count matters.
-__device__ __forceinline__ void umma_bf16_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_mma_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred pe, pa;\n\t"
       "elect.sync _|pe, 0xffffffff;\n\t"
@@ -185,10 +202,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   constexpr uint64_t sbo = (8 * ROW_BYTES) >> 4;
   return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A and B, both
-// K-major, N >> 3 at bit 17, M >> 4 at bit 24
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor) of kind::f16: fp32 accumulate (bit 4), A / B
+// format at bits 7 / 10 (0 = fp16, 1 = bf16), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t instr_desc_fmt(int M, int N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // Swizzle<B,4,3>: 16-byte chunk index (address bits [4,4+B)) ^= address bits [7,7+B)
 template <int ROW_BYTES>
@@ -198,6 +215,7 @@ __device__ __host__ __forceinline__ uint32_t swz(uint32_t off) {
 }
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
+// two fp32 -> packed bf16x2 (a in the low half)
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -207,12 +225,59 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// host: TMA tensor maps (enet_umma.cu)
-bool make_map_e1(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI);   // 4D [N][H][W][CI], box = 128 px
-bool make_map_box(CUtensorMap* m, const bf16* base, int N, int H, int W, int CI, int box_w, int box_rows);
-bool make_map_x(CUtensorMap* m, const bf16* base, size_t pixels, int C);           // 2D [px][C], box [128][64]
-bool make_map_rows(CUtensorMap* m, const bf16* base, size_t pixels, int C, int box_px, int sw);   // 2D [px][C], box [box_px][C]
-// 5D view [N*Ho][2][Wo][2][C] of a [N][2Ho][2Wo][C] tensor (2x2 stride-2 windows), box [rows][1][box_w][1][C]
-bool make_map_window(CUtensorMap* m, const bf16* base, int N, int Ho, int Wo, int C, int rows, int box_w);
+// ---- everything that depends on the 16-bit activation type ------------------------------------
+namespace BC_NS {
+#if BC_ACT_F16
+typedef f16 act_t;
+typedef __half2 act2_t;
+constexpr uint32_t ACT_FMT = 0u;
+constexpr CUtensorMapDataType ACT_TMAP = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+// round to nearest even, saturating at +-65504 instead of overflowing to infinity
+__device__ __forceinline__ uint32_t pack_act(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_act(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+inline uint16_t host_act_bits(float v) {
+  const float lim = 65504.f;
+  __half h = __float2half_rn(v > lim ? lim : v < -lim ? -lim : v);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+#else
+typedef bf16 act_t;
+typedef __nv_bfloat162 act2_t;
+constexpr uint32_t ACT_FMT = 1u;
+constexpr CUtensorMapDataType ACT_TMAP = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+__device__ __forceinline__ uint32_t pack_act(float a, float b) { return pack_bf16(a, b); }
+__device__ __forceinline__ float2 unpack_act(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v)); }
+inline uint16_t host_act_bits(float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return u;
+}
+#endif
+// 0xFFFF per 16-bit lane where b > a (ordered compare)
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t b, uint32_t a) {
+  return __hgt2_mask(*reinterpret_cast<const act2_t*>(&b), *reinterpret_cast<const act2_t*>(&a));
+}
+// A and B operands in the activation type
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) { return instr_desc_fmt(M, N, ACT_FMT); }
+// eight fp32 -> one 16-byte chunk of packed activations
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_act(v[0], v[1]), pack_act(v[2], v[3]), pack_act(v[4], v[5]), pack_act(v[6], v[7]));
+}
 
+// host: TMA tensor maps (enet_umma.cu)
+bool make_map_e1(CUtensorMap* m, const act_t* base, int N, int H, int W, int CI);   // 4D [N][H][W][CI], box = 128 px
+bool make_map_box(CUtensorMap* m, const act_t* base, int N, int H, int W, int CI, int box_w, int box_rows);
+bool make_map_x(CUtensorMap* m, const act_t* base, size_t pixels, int C);           // 2D [px][C], box [128][64]
+bool make_map_rows(CUtensorMap* m, const act_t* base, size_t pixels, int C, int box_px, int sw);   // 2D [px][C], box [box_px][C]
+// 5D view [N*Ho][2][Wo][2][C] of a [N][2Ho][2Wo][C] tensor (2x2 stride-2 windows), box [rows][1][box_w][1][C]
+bool make_map_window(CUtensorMap* m, const act_t* base, int N, int Ho, int Wo, int C, int rows, int box_w);
+
+}  // namespace BC_NS
 }  // namespace bc

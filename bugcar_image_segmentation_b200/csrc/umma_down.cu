@@ -1,4 +1,4 @@
-// First half of an ENet down-sampling bottleneck on tcgen05 (bf16 operands, fp32 accumulation):
+// First half of an ENet down-sampling bottleneck on tcgen05 (fp16 / bf16 operands, fp32 accumulation):
 //
 //   x (full resolution, NHWC) --4 strided TMA box loads (the 2x2 window positions)--> smem
 //        main: max over the four tap tiles + 2-bit argmax (first maximum wins)  -> pooled, idx (global)
@@ -21,14 +21,15 @@
 #include <cstring>
 
 namespace bc {
+namespace BC_NS {
 
 struct DownParams {
   int num_tiles;          // 128-output-pixel tiles
   int reverse;            // 1: walk the tiles from the last to the first (L2 reuse between consecutive kernels, enet_umma.cu)
   int rows_per_tile;      // output rows per tile (128 / Wo, at least 1)
-  bf16* pooled;           // [out px][CIN]
+  act_t* pooled;          // [out px][CIN]
   uint8_t* idx;           // [out px][CIN] window position of the maximum
-  bf16* e1;               // [out px][16]
+  act_t* e1;              // [out px][16]
   const uint8_t* wblob;   // [4 taps][16 rows][CIN] bf16, K-major swizzled rows
   float f[32];            // bias[16], slope[16] (by value: constant-bank operands)
 };
@@ -46,11 +47,9 @@ struct DownSmem {
   static_assert((TOTAL + 2048) * MINB <= 233472, "shared memory budget");
 };
 
-// packed bf16x2 max with argmax update: where b > a (strictly, per 16-bit lane) take b and tap t
+// packed 16-bit x 2 max with argmax update: where b > a (strictly, per 16-bit lane) take b and tap t
 __device__ __forceinline__ void max_arg2(uint32_t& best, uint32_t& bi, uint32_t v, uint32_t t2) {
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&best);
-  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v);
-  const uint32_t m = __hgt2_mask(b, a);               // 0xFFFF per lane where b > a
+  const uint32_t m = gt2_mask(v, best);               // 0xFFFF per lane where b > a
   best = (v & m) | (best & ~m);
   bi = (t2 & m) | (bi & ~m);
 }
@@ -112,7 +111,7 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
       for (int t = 0; t < 4; ++t)
 #pragma unroll
         for (int kk = 0; kk < CIN / 16; ++kk)
-          umma_bf16_e(tmem + b * 16, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP + kk * 32),
+          umma_mma_e(tmem + b * 16, smem_desc<RB>(sbase + S::OFF_TAPS + t * S::TAP + kk * 32),
                     smem_desc<RB>(sbase + S::OFF_W + t * S::WTAP + kk * 32), instr_desc(128, 16), (t | kk) != 0);
       umma_commit_e(bar(TAP_EMPTY));
       umma_commit_e(bar(D_FULL0 + b));
@@ -156,8 +155,8 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j] + p.f[j], p.f[16 + j]);
       uint4* o = reinterpret_cast<uint4*>(p.e1 + px * 16);
-      o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-      o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+      o[0] = pack8(v);
+      o[1] = pack8(v + 8);
     }
   }
   tc_fence_before();
@@ -171,14 +170,17 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
 
 // ------------------------------------------------------------------------ host side
 // w: folded conv [tap = ky*2+kx][cin][ci]; rows beyond ci stay zero (bias 0, slope 1 -> e1 = 0)
-bool down_build(UmmaPack& out, int cin, int ci, const float* w, const float* bias, const float* alpha) {
+}  // namespace BC_NS
+using namespace BC_NS;
+
+bool Umma<act_t>::down_build(UmmaPack& out, int cin, int ci, const float* w, const float* bias, const float* alpha) {
   if ((cin != 16 && cin != 64) || ci > 16) return false;
   const int rb = cin * 2, wtap = 16 * rb;
   std::vector<uint8_t> img(4 * wtap, 0);
   for (int t = 0; t < 4; ++t)
     for (int o = 0; o < ci; ++o)
       for (int k = 0; k < cin; ++k) {
-        __nv_bfloat16 h = __float2bfloat16_rn(w[((size_t)t * cin + k) * ci + o]);
+        const uint16_t h = host_act_bits(w[((size_t)t * cin + k) * ci + o]);
         uint32_t off = (uint32_t)(o * rb + k * 2);
         memcpy(img.data() + t * wtap + (rb == 128 ? swz<128>(off) : swz<32>(off)), &h, 2);
       }
@@ -191,7 +193,7 @@ bool down_build(UmmaPack& out, int cin, int ci, const float* w, const float* bia
 }
 
 template <int CIN>
-static cudaError_t down_launch_t(const UmmaPack& pk, const bf16* x, bf16* pooled, uint8_t* idx, bf16* e1, int n, int Ho, int Wo,
+static cudaError_t down_launch_t(const UmmaPack& pk, const act_t* x, act_t* pooled, uint8_t* idx, act_t* e1, int n, int Ho, int Wo,
                                  int num_sms, cudaStream_t s) {
   using S = DownSmem<CIN>;
   const int rows = 128 / Wo > 0 ? 128 / Wo : 1, box_w = 128 / rows;
@@ -207,20 +209,21 @@ static cudaError_t down_launch_t(const UmmaPack& pk, const bf16* x, bf16* pooled
   p.e1 = e1;
   p.wblob = pk.wblob;
   memcpy(p.f, pk.hf.data(), 32 * sizeof(float));
-  static bool attr_done = false;
-  const int smem = S::TOTAL + 1024;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_down<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  const int smem = S::TOTAL + 1024;        // opt-in set per device by prepare_down()
   const int ctas = num_sms * S::MINB;
   k_umma_down<CIN><<<p.num_tiles < ctas ? p.num_tiles : ctas, 192, smem, s>>>(mx, p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_umma_down(const UmmaPack& pk, const bf16* x, bf16* pooled, uint8_t* idx, bf16* e1, int n, int Ho, int Wo,
-                             int num_sms, cudaStream_t s) {
+cudaError_t Umma<act_t>::prepare_down() {
+  cudaError_t e = cudaFuncSetAttribute(k_umma_down<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DownSmem<64>::TOTAL + 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_umma_down<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DownSmem<16>::TOTAL + 1024);
+  return e;
+}
+
+cudaError_t Umma<act_t>::launch_down(const UmmaPack& pk, const act_t* x, act_t* pooled, uint8_t* idx, act_t* e1, int n, int Ho,
+                                     int Wo, int num_sms, cudaStream_t s) {
   if (pk.C == 64) return down_launch_t<64>(pk, x, pooled, idx, e1, n, Ho, Wo, num_sms, s);
   if (pk.C == 16) return down_launch_t<16>(pk, x, pooled, idx, e1, n, Ho, Wo, num_sms, s);
   return cudaErrorInvalidValue;

@@ -1,6 +1,6 @@
 // ENet head on tcgen05: ConvTranspose2d(16, C, 3, stride 2, padding 1, output_padding 1) +
 // per-pixel class argmax + class LUT (models.py:43-44 tail, models.py:55-58,67 / 78-81), one
-// kernel, bf16 operands, fp32 accumulation, 1 byte per output pixel leaves the SM.
+// kernel, fp16 / bf16 operands, fp32 accumulation, 1 byte per output pixel leaves the SM.
 //
 // Each INPUT pixel (i, j) of the 128x256 map produces the 2x2 output quad (2i+qy, 2j+qx) from
 // its four neighbours (i+di, j+dj): as a GEMM, M = 128 input pixels, K = 4 neighbours x 16
@@ -19,6 +19,7 @@
 #include <cstring>
 
 namespace bc {
+namespace BC_NS {
 
 struct HeadParams {
   int num_tiles;            // B * 128 rows * 2 half-rows
@@ -99,7 +100,7 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < 4; ++t)
-        umma_bf16_e(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (st * 2 + (t >> 1)) * HEAD_SLAB + (t & 1) * 32),
+        umma_mma_e(tmem + b * 64, smem_desc<32>(sbase + HEAD_OFF_TAPS + (st * 2 + (t >> 1)) * HEAD_SLAB + (t & 1) * 32),
                   smem_desc<32>(sbase + HEAD_OFF_W + t * HEAD_WTAP), IDESC, t != 0);
       umma_commit_e(bar(TAP_EMPTY0 + st));
       umma_commit_e(bar(D_FULL0 + b));
@@ -149,7 +150,10 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
 //   W[k][class][ky][kx] when the neighbour reaches quad (qy, qx) (di <= qy, dj <= qx) with
 //   ky = qy ? (di ? 0 : 2) : 1, kx = qx ? (dj ? 0 : 2) : 1;  zero otherwise.
 // w: the folded head weights [ky*3+kx][16][CP] (api.cu), already rounded to bf16 values.
-bool head_build(uint8_t** out, const float* w, int C, int CP) {
+}  // namespace BC_NS
+using namespace BC_NS;
+
+bool Umma<act_t>::head_build(uint8_t** out, const float* w, int C, int CP) {
   std::vector<uint8_t> img(4 * HEAD_WTAP, 0);
   for (int t = 0; t < 4; ++t) {
     int di = t >> 1, dj = t & 1;
@@ -159,7 +163,7 @@ bool head_build(uint8_t** out, const float* w, int C, int CP) {
       int ky = qy ? (di ? 0 : 2) : 1, kx = qx ? (dj ? 0 : 2) : 1;
       for (int c = 0; c < C; ++c)
         for (int k = 0; k < 16; ++k) {
-          __nv_bfloat16 h = __float2bfloat16_rn(w[((size_t)(ky * 3 + kx) * 16 + k) * CP + c]);
+          const uint16_t h = host_act_bits(w[((size_t)(ky * 3 + kx) * 16 + k) * CP + c]);
           uint32_t off = (uint32_t)((q * 16 + c) * 32 + k * 2);
           memcpy(img.data() + t * HEAD_WTAP + swz<32>(off), &h, 2);
         }
@@ -169,8 +173,16 @@ bool head_build(uint8_t** out, const float* w, int C, int CP) {
   return cudaMemcpy(*out, img.data(), img.size(), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
-cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,
-                             int num_sms, cudaStream_t s) {
+cudaError_t Umma<act_t>::prepare_head() {
+  const int smem = HEAD_SMEM + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_umma_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return e;
+}
+
+cudaError_t Umma<act_t>::launch_head(const act_t* x, int B, int C, const uint8_t* wblob, uint8_t* labels, const Lut256& lut,
+                                     int num_sms, cudaStream_t s) {
   CUtensorMap mx;
   if (!make_map_box(&mx, x, B, 128, 256, 16, 129, 1)) return cudaErrorInvalidValue;
   HeadParams p{};
@@ -180,15 +192,7 @@ cudaError_t launch_umma_head(const bf16* x, int B, int C, const uint8_t* wblob, 
   p.wblob = wblob;
   p.labels = labels;
   p.lut = lut;
-  static bool attr_done = false;
-  const int smem = HEAD_SMEM + 1024;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  const int smem = HEAD_SMEM + 1024;       // opt-in set per device by prepare_head()
   int grid = p.num_tiles < 4 * num_sms ? p.num_tiles : 4 * num_sms;
   if (C == 15) k_umma_head<15><<<grid, 192, smem, s>>>(mx, p);          // note_label:1-15
   else if (C == 16) k_umma_head<16><<<grid, 192, smem, s>>>(mx, p);

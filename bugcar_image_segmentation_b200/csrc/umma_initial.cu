@@ -19,11 +19,12 @@
 #include <cstring>
 
 namespace bc {
+namespace BC_NS {
 
 struct InitParams {
   int num_tiles;             // B * 128 * 256 / 128
   const void* x;             // uint8 (B,256,512,3) BGR | float / double (B,3,256,512)
-  bf16* out;                 // (B,128,256,16)
+  act_t* out;                // (B,128,256,16)
   const uint8_t* wblob;      // [hi | lo][16 rows][32 k] tf32 (fp32 bit patterns), 128-byte swizzled rows
   const float* lut;          // [256][3] fp32 normalisation table (RGB order)
   float f[48];               // BN scale g[16], shift b[16], PReLU slope a[16]
@@ -171,8 +172,8 @@ k_umma_initial(const __grid_constant__ InitParams p) {
 #pragma unroll
       for (int o = 0; o < 16; ++o) r[o] = prelu_f(fmaf(r[o], p.f[o], p.f[16 + o]), p.f[32 + o]);
       uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix * 16);
-      o[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
-      o[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+      o[0] = pack8(r);
+      o[1] = pack8(r + 8);
     }
   }
   tc_fence_before();
@@ -246,8 +247,8 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       for (int limb = 0; limb < 3; ++limb)
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          umma_bf16_e(tmem, dA0 + (uint64_t)(kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2), instr_desc(128, 16),
-                      (limb | kk) != 0);
+          umma_mma_e(tmem, dA0 + (uint64_t)(kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2),
+                     instr_desc_fmt(128, 16, 1u), (limb | kk) != 0);   // bytes and weight limbs are bf16 whatever act_t is
       umma_commit_e(bar(D_FULL));
     }
   } else {
@@ -336,8 +337,8 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
 #pragma unroll
       for (int o = 0; o < 16; ++o) r[o] = prelu_f(fmaf(r[o], p.f[o], p.f[16 + o]), p.f[32 + o]);
       uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)out_pix * 16);
-      o[0] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
-      o[1] = make_uint4(pack_bf16(r[8], r[9]), pack_bf16(r[10], r[11]), pack_bf16(r[12], r[13]), pack_bf16(r[14], r[15]));
+      o[0] = pack8(r);
+      o[1] = pack8(r + 8);
     }
   }
   tc_fence_before();
@@ -351,7 +352,10 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
 
 // B image of the uint8 form: three bf16 limbs of  w_k * s_c  (27 columns) and of  sum_c w_(c,tap) * t_c
 // (9 columns), rows = output channels.  w: [27][13] ((c*3+ky)*3+kx major).
-bool initial_build_u8(uint8_t** out, const float* w) {
+}  // namespace BC_NS
+using namespace BC_NS;
+
+bool Umma<act_t>::initial_build_u8(uint8_t** out, const float* w) {
   const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18
   std::vector<uint8_t> img(3 * U8_W, 0);
   auto put = [&](int o, int col, double v) {
@@ -375,7 +379,7 @@ bool initial_build_u8(uint8_t** out, const float* w) {
 }
 
 // w: [27][13] ((c*3+ky)*3+kx major), fp32.  B rows = output channels (13 + 3 zero), K = 32.
-bool initial_build(uint8_t** out, const float* w) {
+bool Umma<act_t>::initial_build(uint8_t** out, const float* w) {
   std::vector<uint8_t> img(2 * INIT_W, 0);
   for (int o = 0; o < 13; ++o)
     for (int k = 0; k < 27; ++k) {
@@ -394,9 +398,18 @@ bool initial_build(uint8_t** out, const float* w) {
   return cudaMemcpy(*out, img.data(), img.size(), cudaMemcpyHostToDevice) == cudaSuccess;
 }
 
-cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const uint8_t* wblob, const uint8_t* wblob_u8,
-                                const float* lut, const float* g, const float* b, const float* a, int num_sms,
-                                cudaStream_t s) {
+cudaError_t Umma<act_t>::prepare_initial() {
+  const int smem = INIT_SMEM + 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_umma_initial<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial_u8, cudaFuncAttributeMaxDynamicSharedMemorySize, U8_SMEM + 1024);
+  return e;
+}
+
+cudaError_t Umma<act_t>::launch_initial(const void* x, int kind, int B, act_t* out, const uint8_t* wblob, const uint8_t* wblob_u8,
+                                        const float* lut, const float* g, const float* b, const float* a, int num_sms,
+                                        cudaStream_t s) {
   InitParams p{};
   p.num_tiles = B * 256;
   p.x = x;
@@ -406,15 +419,7 @@ cudaError_t launch_umma_initial(const void* x, int kind, int B, bf16* out, const
   memcpy(p.f, g, 64);
   memcpy(p.f + 16, b, 64);
   memcpy(p.f + 32, a, 64);
-  const int smem = INIT_SMEM + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_initial<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_initial<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  const int smem = INIT_SMEM + 1024;       // opt-in set per device by prepare_initial()
   if (kind == 0 && ((uintptr_t)x & 3) == 0) {          // the byte-window loads are 32-bit: a frame pointer that is not
     const int ctas8 = num_sms * U8_MINB;               // 4-byte aligned takes the byte-wise tf32 kernel below
     k_umma_initial_u8<<<p.num_tiles < ctas8 ? p.num_tiles : ctas8, 160, U8_SMEM + 1024, s>>>(p);

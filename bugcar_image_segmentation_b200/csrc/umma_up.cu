@@ -1,4 +1,4 @@
-// ENet upsampling bottleneck on tcgen05 (bf16 operands, fp32 accumulation), one kernel:
+// ENet upsampling bottleneck on tcgen05 (fp16 / bf16 operands, fp32 accumulation), one kernel:
 //
 //   x tile (128 low-res pixels, TMA) --G1--> [ main = Wm x | e1 = W1 x ]         D_a [128 x (COUT+CI)]
 //        e1: +bias, act, bf16 -> smem             --G2--> 4 taps of the 2x2 stride-2 transposed conv  D_b [128 x 4 CI]
@@ -16,6 +16,7 @@
 #include <type_traits>
 
 namespace bc {
+namespace BC_NS {
 
 struct UpParams {
   int num_tiles;          // low-resolution 128-pixel tiles
@@ -24,7 +25,7 @@ struct UpParams {
   int Wl;                 // low-resolution width (64 or 128)
   int has_next;
   const uint8_t* idx;     // [low px][COUT] pool window position (2 bits)
-  bf16* e1_next;          // [high px][16]
+  act_t* e1_next;         // [high px][16]
   const uint8_t* wblob;
   // bm[COUT] b1[CI] a1[CI] bt[CI] at[CI] b3[COUT] aout[COUT] b1n[16] a1n[16], by value: constant-bank
   // operands of the epilogue arithmetic (compile-time channel indices), no shared-memory traffic
@@ -135,7 +136,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < CIN / 16; ++kk)
-        umma_bf16_e(tmem + S::COL_A, smem_desc<128>(sbase + S::OFF_X + b * S::XBUF + (kk / 4) * S::XSUB + (kk % 4) * 32),
+        umma_mma_e(tmem + S::COL_A, smem_desc<128>(sbase + S::OFF_X + b * S::XBUF + (kk / 4) * S::XSUB + (kk % 4) * 32),
                   smem_desc<128>(sbase + S::OFF_B1 + (kk / 4) * S::B1_SUB + (kk % 4) * 32), instr_desc(128, S::N1), kk != 0);
       umma_commit_e(bar(X_EMPTY0 + b));
       umma_commit_e(bar(DA_FULL));
@@ -144,7 +145,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < CI / 16; ++kk)
-        umma_bf16_e(tmem + S::COL_B, smem_desc<RB>(sbase + S::OFF_E1 + kk * 32), smem_desc<RB>(sbase + S::OFF_WT + kk * 32),
+        umma_mma_e(tmem + S::COL_B, smem_desc<RB>(sbase + S::OFF_E1 + kk * 32), smem_desc<RB>(sbase + S::OFF_WT + kk * 32),
                   instr_desc(128, 4 * CI), kk != 0);
       umma_commit_e(bar(DB_FULL));
       // G3: expansion of every tap
@@ -154,7 +155,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       for (int t = 0; t < 4; ++t)
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_bf16_e(tmem + S::COL_C + t * COUT, smem_desc<RB>(sbase + S::OFF_E2 + t * S::E_TILE + kk * 32),
+          umma_mma_e(tmem + S::COL_C + t * COUT, smem_desc<RB>(sbase + S::OFF_E2 + t * S::E_TILE + kk * 32),
                     smem_desc<RB>(sbase + S::OFF_W3 + kk * 32), instr_desc(128, COUT), kk != 0);
       umma_commit_e(bar(DC_FULL));
       // G4: next block's projection on the staged high-res rows (COUT == 64: one row = one M tile)
@@ -166,7 +167,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
           for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_e(tmem + S::COL_D + r * 16, smem_desc<128>(sbase + S::OFF_OUT + r * S::OUT_ROW + kk * 32),
+              umma_mma_e(tmem + S::COL_D + r * 16, smem_desc<128>(sbase + S::OFF_OUT + r * S::OUT_ROW + kk * 32),
                         smem_desc<128>(sbase + S::OFF_W1N + kk * 32), instr_desc(128, 16), kk != 0);
           umma_commit_e(bar(DD_FULL));
         }
@@ -196,8 +197,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
 #pragma unroll
           for (int c = 0; c < 2; ++c)
             *reinterpret_cast<uint4*>(smem + S::OFF_E1 + swz<RB>(m * RB + (2 * h + c) * 16)) =
-                make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+                pack8(v + 8 * c);
         };
         if (eh == 0) ep_a(std::integral_constant<int, 0>{}); else ep_a(std::integral_constant<int, 1>{});
       } else {
@@ -208,8 +208,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
           *reinterpret_cast<uint4*>(smem + S::OFF_E1 + swz<RB>(m * RB + c * 16)) =
-              make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                         pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+              pack8(v + 8 * c);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -226,8 +225,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
 #pragma unroll
         for (int c = 0; c < CI / 8; ++c)
           *reinterpret_cast<uint4*>(smem + S::OFF_E2 + t * S::E_TILE + swz<RB>(m * RB + c * 16)) =
-              make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                         pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+              pack8(v + 8 * c);
       }
       fence_proxy_async();
       tc_fence_before();
@@ -254,7 +252,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
           for (int j = 0; j < 16; j += 2) {
             float o0 = prelu_f(v[j] + p.f[F_B3 + c0 + j] + (ib[j] == t ? mainv[j] : 0.f), p.f[F_AOUT + c0 + j]);
             float o1 = prelu_f(v[j + 1] + p.f[F_B3 + c0 + j + 1] + (ib[j + 1] == t ? mainv[j + 1] : 0.f), p.f[F_AOUT + c0 + j + 1]);
-            pk[j / 2] = pack_bf16(o0, o1);
+            pk[j / 2] = pack_act(o0, o1);
           }
           // high-res pixel (2*lr + ky, 2*lx + kx) of this tile
           const int hr = 2 * lr + (t >> 1), hx = 2 * lx + (t & 1);
@@ -291,8 +289,8 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = prelu_f(v[j] + p.f[F_B1N + j], p.f[F_A1N + j]);
             uint4* o = reinterpret_cast<uint4*>(p.e1_next + ((hrow0 + r) * Wh + m) * 16);
-            o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-            o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            o[0] = pack8(v);
+            o[1] = pack8(v + 8);
           }
           tc_fence_before();
         }
@@ -319,7 +317,7 @@ static void put_rows(uint8_t* dst, int rows, int row_bytes, int sw, const float*
   // element (row r, k) = w[r * stride_row + (k0 + k) * stride_k]
   for (int r = 0; r < rows; ++r)
     for (int k = 0; k < row_bytes / 2; ++k) {
-      __nv_bfloat16 h = __float2bfloat16_rn(w[(size_t)r * stride_row + (size_t)(k0 + k) * stride_k]);
+      const uint16_t h = host_act_bits(w[(size_t)r * stride_row + (size_t)(k0 + k) * stride_k]);
       uint32_t off = (uint32_t)(r * row_bytes + k * 2);
       uint32_t so = sw == 128 ? swz<128>(off) : sw == 64 ? swz<64>(off) : swz<32>(off);
       memcpy(dst + so, &h, 2);
@@ -359,8 +357,14 @@ static bool up_build_t(UmmaPack& out, const float* wm, const float* bmv, const f
   return true;
 }
 
+template <int CIN, int CI, int COUT>
+static cudaError_t up_launch_t(const UmmaPack& pk, const act_t* x, const uint8_t* idx, act_t* y, act_t* e1_next, int n, int Hl,
+                               int Wl, int has_next, int num_sms, cudaStream_t s);
+}  // namespace BC_NS
+using namespace BC_NS;
+
 // NB: a row of put_rows' source walks `stride_row` = 1 (out channel contiguous in [cin][cout]).
-bool up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const float* bm, const float* w1, const float* b1,
+bool Umma<act_t>::up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const float* bm, const float* w1, const float* b1,
               const float* a1, const float* wt, const float* bt, const float* at, const float* w3, const float* b3,
               const float* aout, const float* w1n, const float* b1n, const float* a1n) {
   if (cin == 128 && ci == 32 && cout == 64)
@@ -370,8 +374,9 @@ bool up_build(UmmaPack& out, int cin, int ci, int cout, const float* wm, const f
   return false;
 }
 
+namespace BC_NS {
 template <int CIN, int CI, int COUT>
-static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t* idx, bf16* y, bf16* e1_next, int n, int Hl,
+static cudaError_t up_launch_t(const UmmaPack& pk, const act_t* x, const uint8_t* idx, act_t* y, act_t* e1_next, int n, int Hl,
                                int Wl, int has_next, int num_sms, cudaStream_t s) {
   using S = UpSmem<CIN, CI, COUT>;
   CUtensorMap mx, my;
@@ -389,13 +394,7 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
   p.e1_next = e1_next;
   p.wblob = pk.wblob;
   memcpy(p.f, pk.hf.data(), pk.hf.size() * sizeof(float));
-  static bool attr_done = false;
-  const int smem = S::TOTAL + 1024;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_up<CIN, CI, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  const int smem = S::TOTAL + 1024;        // opt-in set per device by prepare_up()
   static_assert((S::TOTAL + 2048) * S::MINB <= 233472 && S::TMEM_COLS * S::MINB <= 512, "CTAs per SM");
   const int ctas = num_sms * S::MINB;                    // upsample5_0 fits three times per SM: three tiles in flight
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
@@ -403,8 +402,18 @@ static cudaError_t up_launch_t(const UmmaPack& pk, const bf16* x, const uint8_t*
   return cudaGetLastError();
 }
 
-cudaError_t launch_umma_up(const UmmaPack& pk, int cin, int cout, const bf16* x, const uint8_t* idx, bf16* y, bf16* e1_next,
-                           int n, int Hl, int Wl, int has_next, int num_sms, cudaStream_t s) {
+}  // namespace BC_NS
+
+cudaError_t Umma<act_t>::prepare_up() {
+  cudaError_t e = cudaFuncSetAttribute(k_umma_up<128, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       UpSmem<128, 32, 64>::TOTAL + 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_umma_up<64, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, UpSmem<64, 16, 16>::TOTAL + 1024);
+  return e;
+}
+
+cudaError_t Umma<act_t>::launch_up(const UmmaPack& pk, int cin, int cout, const act_t* x, const uint8_t* idx, act_t* y,
+                                   act_t* e1_next, int n, int Hl, int Wl, int has_next, int num_sms, cudaStream_t s) {
   if (cin == 128 && cout == 64 && Wl == 64) return up_launch_t<128, 32, 64>(pk, x, idx, y, e1_next, n, Hl, Wl, has_next, num_sms, s);
   if (cin == 64 && cout == 16 && Wl == 128) return up_launch_t<64, 16, 16>(pk, x, idx, y, e1_next, n, Hl, Wl, 0, num_sms, s);
   return cudaErrorInvalidValue;

@@ -57,7 +57,7 @@ class ENET(InferenceModel):
 
     _shared_pre = {}                             # device -> Context used by the classmethod preprocess
 
-    def __init__(self, GRAPH_PB_PATH=None, device=None, max_batch=None, precision="bf16"):
+    def __init__(self, GRAPH_PB_PATH=None, device=None, max_batch=None, precision="fp16"):
         torch, dev = runtime.torch_cuda(device)
         self._torch, self.device = torch, dev
         if GRAPH_PB_PATH is None:
@@ -71,9 +71,11 @@ class ENET(InferenceModel):
                              "to a .bcw container first")
         with open(GRAPH_PB_PATH, "rb") as f:     # models.py:25-26
             blob = f.read()
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         self.ctx = runtime.new_context(dev, max_batch)
+        self.ctx.set_precision(_lib.PRECISIONS[precision])      # before the load: weights are packed once
         self.ctx.load_enet(blob)
-        self.ctx.set_precision(_lib.BC_PREC_FP32 if precision in ("fp32", "float32") else _lib.BC_PREC_BF16)
         self.num_classes = self.ctx.num_classes()
         self.test = None                         # models.py:31
 

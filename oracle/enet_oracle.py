@@ -29,14 +29,15 @@ class _Net:
     def __init__(self, weights, bn_eps=BN_EPS, emulate=None, calibrate=False):
         self.w = {k: _t(v) for k, v in weights.items()}
         self.eps = bn_eps
-        self.emulate = emulate
+        self.emulate = emulate            # None | "bf16" | "fp16": the 16-bit storage type to emulate
+        self.qdtype = {None: None, "bf16": torch.bfloat16, "fp16": torch.float16}[emulate]
         self.calibrate = calibrate   # tools/make_weights.py: set BN running stats from data
 
     # ---- helpers
     def q(self, x):
         """activation storage rounding"""
-        if self.emulate == "bf16":
-            return x.to(torch.bfloat16).to(torch.float32)
+        if self.emulate:
+            return x.to(self.qdtype).to(torch.float32)
         return x
 
     def act(self, x, name):
@@ -57,13 +58,13 @@ class _Net:
         """conv (no bias) followed by eval-mode BN.  In bf16 emulation the BN is
         folded into bf16 weights + fp32 bias, as the CUDA loader does."""
         W = self.w[conv + ".weight"]
-        if self.emulate == "bf16":
+        if self.emulate:
             g = self.w[bn + ".weight"] / torch.sqrt(self.w[bn + ".running_var"] + self.eps)
             b = self.w[bn + ".bias"] - self.w[bn + ".running_mean"] * g
             if transposed:
-                Wf = (W * g.view(1, -1, 1, 1)).to(torch.bfloat16).to(torch.float32)
+                Wf = (W * g.view(1, -1, 1, 1)).to(self.qdtype).to(torch.float32)
                 return F.conv_transpose2d(x, Wf, b, **kw)
-            Wf = (W * g.view(-1, 1, 1, 1)).to(torch.bfloat16).to(torch.float32)
+            Wf = (W * g.view(-1, 1, 1, 1)).to(self.qdtype).to(torch.float32)
             return F.conv2d(x, Wf, b, **kw)
         y = F.conv_transpose2d(x, W, None, **kw) if transposed else F.conv2d(x, W, None, **kw)
         return self.bn(y, bn)
@@ -123,8 +124,8 @@ class _Net:
                 x = self.up(x, name, pool_idx[src], sizes[src])
             inter[name] = x
         W = self.w["transposed_conv.weight"]
-        if self.emulate == "bf16":
-            W = W.to(torch.bfloat16).to(torch.float32)
+        if self.emulate:
+            W = W.to(self.qdtype).to(torch.float32)
         logits = F.conv_transpose2d(x, W, None, stride=2, padding=1, output_padding=1)
         if return_intermediates:
             return logits, inter

@@ -6,9 +6,12 @@ TensorFlow graph (blob absent, see oracle/__init__.py); tolerances:
     |d| <= 1e-4 * max|logit| on >= 99 % of elements (the rest are max-unpool index flips: two
     window values within 1 fp32 ulp order differently under a different summation order, and
     the moved activation spreads through the decoder's 3x3 convs); argmax agreement >= 99.9 %
-  * bf16 mode  vs bf16-emulating oracle (same rounding points): max|d| <= 2^-6 * max|logit|
-    on 99.9 % of logits, argmax agreement >= 99.9 % of pixels whose top-2 margin exceeds
-    the error bound; raw agreement reported
+  * fp16 mode (production, tcgen05) vs the FP32 oracle: RAW per-pixel argmax agreement >= 99.9 %
+    for the trained-like weights, no margin filter (north_star's bar); logits vs the
+    fp16-emulating oracle (same rounding points) |d| <= 2^-9 * max|logit| on 99.9 % of logits
+  * bf16 mode  vs bf16-emulating oracle: max|d| <= 2^-6 * max|logit| on 99.9 % of logits, argmax
+    agreement >= 99.9 % of pixels whose top-2 margin exceeds the error bound; its raw agreement
+    with the fp32 oracle is 99.7 % (reported; the reason fp16 is the production storage type)
   * fused labels == argmax+LUT of the same mode's logits, bit-exact
   * grids bit-exact given the label map
 """
@@ -46,7 +49,7 @@ def setup(request):
     frames = _frames(which, 3)
     x = np.concatenate([pre_oracle.preprocess(f) for f in frames])
     want32 = enet_oracle.forward(w, x, eps)
-    want16 = enet_oracle.forward(w, x, eps, emulate="bf16")
+    want16 = {e: enet_oracle.forward(w, x, eps, emulate=e) for e in ("bf16", "fp16")}
     model = ENET(WEIGHTS[which], device=0, max_batch=8)
     return dict(which=which, model=model, frames=frames, x=x, want32=want32, want16=want16)
 
@@ -104,26 +107,28 @@ def test_fp32_encoder_blocks_exact(setup):
             assert np.percentile(d, 99) <= 1e-4, (name, np.percentile(d, 99))
 
 
-def test_bf16_logits_and_argmax(setup):
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_16bit_logits_and_argmax(setup, mode):
     from bugcar_image_segmentation_b200 import _lib
     from oracle import pre_oracle
     m = setup["model"]
-    m.ctx.set_precision(_lib.BC_PREC_BF16)
+    m.ctx.set_precision(_lib.PRECISIONS[mode])
+    rel_tol = 2.0 ** -9 if mode == "fp16" else 2.0 ** -6     # 8 x more significand bits in fp16
     for tc in (0, 1):
         m.ctx.set_tensor_cores(tc)
         got = m.logits(setup["x"])
-        want = setup["want16"]
+        want = setup["want16"][mode]
         scale = np.abs(want).max()
         d = np.abs(got - want)
-        tol = 2.0 ** -6 * scale
+        tol = rel_tol * scale
         frac_ok = (d <= tol).mean()
         a, b = got.argmax(1), want.argmax(1)
         raw = (a == b).mean()
         big = _margin(want) > 2 * tol
         conf = (a == b)[big].mean()
         raw32 = (a == setup["want32"].argmax(1)).mean()
-        print(f"[{setup['which']} tc={tc}] bf16 vs emulated oracle: within-tol {frac_ok:.5f}, argmax raw {raw:.5f}, "
-              f"confident ({big.mean():.3f} of px) {conf:.5f}; vs fp32 oracle raw {raw32:.5f}")
+        print(f"[{setup['which']} {mode} tc={tc}] vs emulated oracle: within-tol {frac_ok:.5f}, argmax raw {raw:.5f}, "
+              f"confident ({big.mean():.3f} of px) {conf:.5f}; vs FP32 oracle raw {raw32:.5f}")
         # the random-weight net is chaotic (max-unpool flips on white-noise features): 99 % there
         assert frac_ok >= (0.999 if setup["which"] == "trained" else 0.99), frac_ok
         assert conf >= 0.999, conf
@@ -138,22 +143,26 @@ def test_bf16_logits_and_argmax(setup):
             diff = lab != ref_lab
             assert diff.mean() <= 1e-4, diff.mean()
             assert (_margin(got)[diff] <= 1e-4 * scale).all()
-    if setup["which"] == "trained":
-        # a trained-like network keeps its decisions under bf16 storage
-        assert raw32 >= 0.99, raw32
+        if setup["which"] == "trained":
+            # north_star: >= 99.9 % per-pixel argmax agreement with the fp32 network -- RAW, every pixel counted,
+            # tensor cores on and off.  bf16 storage cannot reach it (99.7 %), which is why fp16 is the default.
+            assert raw32 >= (0.999 if mode == "fp16" else 0.99), (mode, tc, raw32)
+            lab32 = pre_oracle.labels_from_logits(setup["want32"], pre_oracle.LUT_3WAY)
+            assert (lab == lab32).mean() >= (0.999 if mode == "fp16" else 0.99)
+    m.ctx.set_precision(_lib.BC_PREC_FP16)
 
 
 def test_labels_same_for_all_input_kinds_and_chunks(setup):
     from bugcar_image_segmentation_b200 import _lib
     m = setup["model"]
-    m.ctx.set_precision(_lib.BC_PREC_BF16)
+    m.ctx.set_precision(_lib.BC_PREC_FP16)
     base = m.predict(setup["frames"])
     # fp64 / fp32 NCHW inputs take the same kernel with the same fp32 operands: identical labels
     from_f64 = m.predict(setup["x"])
     assert np.array_equal(m.predict(setup["x"].astype(np.float32)), from_f64)
     # uint8 frames fold the normalisation into the weights (s*u + t, exact bytes as operands): equal to
-    # the float path up to fp32 round-off, i.e. labels may differ only at bf16 rounding ties
-    # (the random-weight net is chaotic -- a one-ulp bf16 flip in the first block moves max-pool indices
+    # the float path up to fp32 round-off, i.e. labels may differ only at 16-bit rounding ties
+    # (the random-weight net is chaotic -- a one-ulp 16-bit flip in the first block moves max-pool indices
     # downstream -- so only the trained-like weights give a meaningful bound)
     assert (from_f64 == base).mean() >= (0.9995 if setup["which"] == "trained" else 0.9), (from_f64 == base).mean()
     for chunk in (1, 2, 0):
@@ -172,7 +181,7 @@ def test_pipeline_equals_staged_calls(setup, cal):
     from bugcar_image_segmentation_b200.pipeline import FramePipeline
     from oracle import bev_oracle
     m = setup["model"]
-    m.ctx.set_precision(_lib.BC_PREC_BF16)
+    m.ctx.set_precision(_lib.BC_PREC_FP16)
     c = synth.calibration(cal)
     bev = bev_transform_tools(c["input image size"], c["output image size"], c["distance to target"],
                               c["tile_length"], c["cm_per_px"], c["yaw"], c["is_laserscan"])
@@ -209,7 +218,7 @@ def test_pipeline_resizes_camera_frames(setup):
     from bugcar_image_segmentation_b200.bev import bev_transform_tools
     from bugcar_image_segmentation_b200.pipeline import FramePipeline
     m = setup["model"]
-    m.ctx.set_precision(_lib.BC_PREC_BF16)
+    m.ctx.set_precision(_lib.BC_PREC_FP16)
     c = synth.calibration("B")
     bev = bev_transform_tools(c["input image size"], c["output image size"], c["distance to target"],
                               c["tile_length"], c["cm_per_px"], c["yaw"], c["is_laserscan"])
@@ -254,6 +263,77 @@ def test_full_batch_properties(setup):
     assert big.ctx.launch_count() > 0
 
 
+def test_bs256_distinct_frames_vs_oracle():
+    """BASELINE config 2 as the bench runs it: ONE batch of 256 DISTINCT frames (128 colour-region scenes, 64
+    blocky, 64 white noise) through the production mode (fp16 storage, tcgen05, bs-256 launch geometry:
+    every CTA walks several tiles, all ring / parity wrap-arounds happen), graphs on and off.  The oracle
+    (torch fp32 on CPU) is evaluated on 10 sampled frames including the first and the last of the batch
+    (= the first and last tiles of every kernel).  Trained-like weights: RAW argmax agreement >= 99.9 % on
+    the scene frames, no margin filter."""
+    import torch
+    from bugcar_image_segmentation_b200.models import ENET
+    from bugcar_image_segmentation_b200.bev import bev_transform_tools
+    from bugcar_image_segmentation_b200.pipeline import FramePipeline
+    from oracle import pre_oracle, enet_oracle, bev_oracle
+    w, nc, eps = _load("trained")
+    frames = np.empty((256, 256, 512, 3), np.uint8)
+    for i in range(256):
+        frames[i] = (synth.region_frame(3000 + i)[0] if i % 2 == 0 else
+                     synth.blocky_frame(3000 + i) if i % 4 == 1 else synth.noise_frame(3000 + i))
+    sample = [0, 1, 2, 3, 126, 128, 191, 253, 254, 255]
+    x = np.concatenate([pre_oracle.preprocess(frames[i]) for i in sample])
+    want = enet_oracle.forward(w, x, eps)
+    want_cls = want.argmax(1)
+    big = ENET(WEIGHTS["trained"], device=0, max_batch=256)              # default precision: fp16
+    d = torch.from_numpy(frames).cuda()
+    ident = np.arange(256, dtype=np.uint8)
+    cls = big.predict_device(d, lut=ident).cpu().numpy()                 # raw class map, fused head
+    agree = np.array([(cls[i] == want_cls[k]).mean() for k, i in enumerate(sample)])
+    scene = np.array([i % 2 == 0 for i in sample])
+    print("bs256 raw argmax agreement vs fp32 oracle per sampled frame:", dict(zip(sample, np.round(agree, 5))))
+    assert agree[scene].mean() >= 0.999, agree
+    assert agree[scene].min() >= 0.998, agree
+    # out-of-distribution inputs (blocky / white noise) give the trained net many near-ties: looser, but not chaos
+    assert agree[~scene].min() >= 0.97, agree
+    # same frames in another batch position and at batch 10 give the same classes (frame independence)
+    small = big.predict_device(torch.from_numpy(frames[sample]).cuda(), lut=ident).cpu().numpy()
+    assert np.array_equal(small, cls[sample])
+    # whole pipeline at bs 256, graphs on and off: labels == the 3-way LUT of those classes, grids bit-exact given them
+    c = synth.calibration("A")
+    bev = bev_transform_tools(c["input image size"], c["output image size"], c["distance to target"],
+                              c["tile_length"], c["cm_per_px"], c["yaw"], c["is_laserscan"])
+    bev._bev_matrix = np.asarray(c["bev matrix"]).reshape(3, 3)
+    pipe = FramePipeline(big, bev, 10.0, 10.0, 0.1)
+    ww, wh = c["output image size"]
+    for graphs in (1, 0):
+        big.ctx.set_graphs(graphs)
+        d_lab = torch.zeros((256, 256, 512), dtype=torch.uint8, device="cuda")
+        grids = pipe.run_device(d, d_labels=d_lab).cpu().numpy()
+        lab = d_lab.cpu().numpy()
+        assert np.array_equal(lab, ENET.LUT_3WAY[cls]), graphs
+        for i in sample:
+            ref = bev_oracle.occupancy_grid(lab[i], c["bev matrix"], ww, wh, c["cm_per_px"], 10.0, 10.0, 0.1)
+            assert np.array_equal(grids[i], ref), (graphs, i)
+    big.ctx.set_graphs(1)
+
+
+@pytest.mark.parametrize("B", [193, 199, 211, 233, 255])
+def test_odd_batch_sizes_in_the_race_regime(B):
+    """Batch sizes 193..255 (where round 1's x-ring race showed up): the batch result equals the same frames
+    pushed through in chunks of 7, frame by frame."""
+    import torch
+    from bugcar_image_segmentation_b200.models import ENET
+    m = ENET(WEIGHTS["trained"], device=0, max_batch=256)
+    base = np.stack([synth.region_frame(4000 + i)[0] for i in range(8)] + [synth.noise_frame(4100 + i) for i in range(4)])
+    idx = (np.arange(B) * 7 + B) % len(base)
+    d = torch.from_numpy(base[idx]).cuda()
+    ident = np.arange(256, dtype=np.uint8)
+    got = m.predict_device(d, lut=ident).cpu().numpy()
+    m.ctx.set_chunk(7)
+    ref = m.predict_device(torch.from_numpy(base).cuda(), lut=ident).cpu().numpy()
+    assert np.array_equal(got, ref[idx])
+
+
 def test_streaming_host_entry_point(setup):
     """bc_pipeline_host_submit / _wait (two staging slots, copy/compute overlap across steps)
     returns the same grids as the blocking bc_pipeline_host, step after step."""
@@ -262,7 +342,7 @@ def test_streaming_host_entry_point(setup):
     from bugcar_image_segmentation_b200.bev import bev_transform_tools
     from bugcar_image_segmentation_b200.pipeline import FramePipeline
     m = setup["model"]
-    m.ctx.set_precision(_lib.BC_PREC_BF16)
+    m.ctx.set_precision(_lib.BC_PREC_FP16)
     c = synth.calibration("A")
     bev = bev_transform_tools(c["input image size"], c["output image size"], c["distance to target"],
                               c["tile_length"], c["cm_per_px"], c["yaw"], c["is_laserscan"])
