@@ -108,19 +108,30 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def base_frames(rank, k):
+    """the 32 distinct frames of rank `rank`'s input set k; frame i of the batch is base[i % 32]"""
+    from bugcar_image_segmentation_b200 import synth
+    s0 = 1234 + k * 100000 + rank * BATCH
+    if FRAMES == "scene":
+        return np.stack([synth.region_frame(s0 + i)[0] for i in range(32)])
+    return synth.frames(32, s0)
+
+
 def make_frames(rank, n_sets):
     """frame i of rank r in set k: seed 1234 + k*100000 + r*BATCH + i.
     Generating 1024 seeded frames with NumPy takes a while; build 32 per set and tile."""
-    from bugcar_image_segmentation_b200 import synth
-    sets = []
-    for k in range(n_sets):
-        s0 = 1234 + k * 100000 + rank * BATCH
-        if FRAMES == "scene":
-            base = np.stack([synth.region_frame(s0 + i)[0] for i in range(32)])
-        else:
-            base = synth.frames(32, s0)
-        sets.append(np.ascontiguousarray(np.tile(base, (BATCH // 32, 1, 1, 1))))
-    return sets
+    return [np.ascontiguousarray(np.tile(base_frames(rank, k), (BATCH // 32, 1, 1, 1))) for k in range(n_sets)]
+
+
+# SURVEY.md 8(a) block-I/O model: bytes per frame a launch must move (block input once + block output once, 16-bit
+# activations, 1-byte pool indices); an asymmetric block's I/O is booked on its second launch.  Sum = 42.3 MB/frame.
+BLOCKIO_BYTES_PER_FRAME = {
+    "umma_initial": 393216 + 1048576, "umma_pool_conv16": 0, "umma_down64": 1048576 + 1048576 + 131072,
+    "umma_bottleneck64": 2097152, "umma_pool_conv64": 0, "umma_down128": 1048576 + 524288 + 131072,
+    "umma_bottleneck128": 1048576, "umma_conv5x1": 0, "umma_bottleneck128_asym": 1048576,
+    "umma_up4": 524288 + 1048576 + 131072, "umma_up5": 1048576 + 1048576 + 131072, "stage5_bottleneck": 2097152,
+    "umma_head_argmax_lut": 1048576 + 131072, "occgrid": 131072 + 10000,
+}
 
 
 def workload_config(B):
@@ -355,11 +366,30 @@ def main():
                    (lambda: [e.synchronize() for e in done]))
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     e2e = world * B * args.steps / (ms_e2e / 1e3)
-    step_e2e(0)                                          # untimed: grids of input set 0 for the CPU cross-check
+    step_e2e(0)                                          # untimed: grids of input set 0 for the cross-checks
     if world == 1:
         model.ctx.pipeline_host_wait(0)
+    else:
+        for e in done:
+            e.synchronize()
     torch.cuda.synchronize()
     grids_check = pinned_out.numpy()[:B].copy()
+
+    # ---- N > 1: what rank 0 holds after the gather == what one GPU computes for the same frames.  Rank 0
+    # regenerates 8 sampled frames of EVERY rank's input set 0 (seeds are a function of the rank), pushes them
+    # through its own pipeline and compares with the rows of the gathered host buffer.
+    gather_check = None
+    if world > 1:
+        if rank == 0:
+            gathered_host = pinned_out.numpy()
+            idx = np.array([0, 31, 32, 63, 128, 200, 254, 255]) % B
+            ok = True
+            for r in range(world):
+                fr = base_frames(r, 0)[idx % 32]
+                want = pipe.run_device(torch.from_numpy(np.ascontiguousarray(fr)).cuda()).cpu().numpy()
+                ok = ok and bool(np.array_equal(gathered_host[r * B + idx], want))
+            gather_check = ok
+        barrier()
 
     # ---- per-kernel profile (events around every launch), rank 0 at any N
     roofline, kernels = None, None
@@ -384,13 +414,31 @@ def main():
             for k in kernels:
                 k["dram_bytes_per_launch_ncu"] = tj.get(k["kernel"], {}).get("dram_bytes_per_launch")
             traffic = top.get("dram_bytes_per_launch_ncu")
-        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm, "unit": "GB/s",
-                    "frac": top["gbs"] / hbm, "traffic": traffic, "peak_source": which,
-                    "share_of_step": top["share"], "avg_launch_us": top["ms"] * 1e3 / top["launches"],
-                    "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
-                    "whole_path": {"algorithmic_gbs": sum(k["bytes"] for k in kernels) / (tot * 1e-3) / 1e9,
-                                   "frac": sum(k["bytes"] for k in kernels) / (tot * 1e-3) / 1e9 / hbm,
-                                   "tflops": sum(k["flops"] for k in kernels) / (tot * 1e-3) / 1e12}}
+        for k in kernels:
+            k["blockio_bytes_per_launch"] = BLOCKIO_BYTES_PER_FRAME.get(k["kernel"], 0) * B
+        top_us = top["ms"] * 1e3 / top["launches"]
+        blockio_gbs = top["blockio_bytes_per_launch"] / (top_us * 1e-6) / 1e9
+        step_s = ms / args.steps * 1e-3                 # the TIMED device-resident step, not the profiling pass
+        n_prof_steps = max(2, min(args.steps, 5))
+        own_bytes_per_step = sum(k["bytes"] for k in kernels) / n_prof_steps
+        blockio_per_step = sum(k["blockio_bytes_per_launch"] * k["launches"] for k in kernels) / n_prof_steps
+        # `achieved` / `frac`: SURVEY 8(a)/(d) block-I/O bytes (x in + y out) of one launch / its average duration.
+        # `frac_own_model` also counts the quarter-width e1 in / e1' out that exist because the block spans two
+        # kernels; `dram_frac` uses the DRAM bytes ncu measured for this kernel (profiles/traffic.json).
+        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": blockio_gbs, "peak": hbm, "unit": "GB/s",
+                    "frac": blockio_gbs / hbm, "frac_blockio": blockio_gbs / hbm, "frac_own_model": top["gbs"] / hbm,
+                    "dram_frac": (traffic / (top_us * 1e-6) / 1e9 / hbm) if traffic else None,
+                    "traffic": traffic, "peak_source": which,
+                    "share_of_step": top["share"], "avg_launch_us": top_us,
+                    "algorithmic_bytes_per_launch": top["blockio_bytes_per_launch"],
+                    "own_model_bytes_per_launch": top["bytes"] / top["launches"],
+                    "whole_path": {"timed_step_ms": ms / args.steps,
+                                   "blockio_mb_per_frame": blockio_per_step / B / 1e6,
+                                   "blockio_gbs": blockio_per_step / step_s / 1e9,
+                                   "frac_blockio": blockio_per_step / step_s / 1e9 / hbm,
+                                   "own_model_mb_per_frame": own_bytes_per_step / B / 1e6,
+                                   "frac_own_model": own_bytes_per_step / step_s / 1e9 / hbm,
+                                   "tflops": sum(k["flops"] for k in kernels) / n_prof_steps / step_s / 1e12}}
 
     # ---- batch-1 streaming latency (BASELINE config 3) on rank 0 of a 1-GPU run
     latency = None
@@ -533,7 +581,7 @@ def main():
                        chunk=args.chunk, tensor_cores=not args.no_tc),
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "gather_check": gather_check, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "latency_bs1": latency, "contour_filter": contour, "laserscan": laser, "config5_postprocessing": config5,
             "kernels": kernels,
         }))

@@ -106,6 +106,7 @@ struct bc_ctx {
   uint8_t* d_head_umma = nullptr;     // tcgen05 operand image of the head (bf16 mode, C <= 16)
   uint8_t* d_init_umma = nullptr;     // tcgen05 operand images of the initial block (bf16 mode): float inputs,
   uint8_t* d_init_umma_u8 = nullptr;  // uint8 frames
+  float init_u8_unscale[16] = {0};    // power-of-two un-scale per output channel of the uint8 operand image
   // normalisation LUTs (models.py:91): [256][3] RGB order
   float* d_lut32 = nullptr;
   double* d_lut64 = nullptr;
@@ -545,7 +546,7 @@ int build_umma_packs(bc_ctx* c) {
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
     }
-    if (!U::initial_build(&c->d_init_umma, c->h_init_w.data()) || !U::initial_build_u8(&c->d_init_umma_u8, c->h_init_w.data()))
+    if (!U::initial_build(&c->d_init_umma, c->h_init_w.data()) || !U::initial_build_u8(&c->d_init_umma_u8, c->h_init_w.data(), c->init_u8_unscale))
       return fail(c, BC_ERR_CUDA, "building the tcgen05 initial-block operands failed");
     if (c->num_classes <= 16) {
       std::vector<float> hw(c->h_full_w.size());
@@ -658,7 +659,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
     if constexpr (is16<T>::value) {
       cudaError_t ce = cudaSuccess;
       L(c, "umma_initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
-        ce = Umma<T>::launch_initial(x, kind, n, X, c->d_init_umma, c->d_init_umma_u8, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
+        ce = Umma<T>::launch_initial(x, kind, n, X, c->d_init_umma, c->d_init_umma_u8, c->init_u8_unscale, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
                                  c->h_init_a.data(), c->num_sms, s);
       });
       if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 initial-block launch: ") + cudaGetErrorString(ce));

@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 namespace bc {
 namespace BC_NS {
@@ -42,6 +43,9 @@ struct UmmaParams {
   int reverse;          // 1: walk the tiles from the last to the first (see launch_one: L2 reuse between consecutive kernels)
   int vslab;            // 1: 5x1 conv on a full-width two-row tile: ONE 6-row box per tile, ky taps = descriptors 64 pixels apart
   int rowslab;          // 1: 3x3 dilation-1 conv on a one-row tile: 3 row loads of 130 pixels, kx through shifted descriptors
+  int pairslab;         // 1: 3x3 (any dilation) / 1x5 conv on a two-row tile of a 64-wide map: one pixel-interleaved slab per kernel row (see below)
+  int pair_step;        // pair-slab: pixels between two kernel columns (the dilation; 1 for 1x5)
+  int pair_halo;        // pair-slab: pixels left of the tile in the slab (dilation, or 2 for 1x5)
   int has_next;         // 1: compute the next block's projection from the y tile
   act_t* out_small;     // e2 (conv-only specialisation) or e1' (has_next): [pixels][CI]
   const uint8_t* wblob; // packed weights, exact shared-memory image (see UmmaSmem)
@@ -70,12 +74,13 @@ struct UmmaWeights {
 // < C: down-sampling bottleneck), NG = epilogue groups per CTA (tiles in flight), MINB = CTAs per SM
 // CONV: conv-only specialisation (first half of an asymmetric bottleneck: taps -> e2 in global memory);
 // no residual / y tiles, no e2 tile, only the conv weights: small enough for two CTAs per SM
-template <int C, int CI, int CN, int CRES, int NG_, int MINB_, bool CONV = false>
+template <int C, int CI, int CN, int CRES, int NG_, int MINB_, bool CONV = false, int EPW_ = 1>
 struct UmmaSmem {
   using Wt = UmmaWeights<C, CI, CN>;
   static constexpr int NG = NG_, MINB = MINB_;
   static constexpr bool NARROW = CRES < C;
-  static constexpr int THREADS = 128 + 128 * NG;
+  static constexpr int EPW = EPW_;                  // warps per TMEM lane quarter of an epilogue group
+  static constexpr int THREADS = 128 + 128 * NG * EPW;
   static constexpr int RB = CI * 2;
   static constexpr int TAP_BYTES = 128 * RB;        // one A tap tile
   // ring slot: a tap tile, or (row-slab mode, CI = 16) one image row of 128 + 2 pixels, padded to the 32-byte-swizzle repeat
@@ -84,16 +89,26 @@ struct UmmaSmem {
   static constexpr int XSUB = 128 * 128;            // one 64-channel sub-tile of x / y
   static constexpr int NSUB = C / 64;
   static constexpr int XBUF = NSUB * XSUB;          // one x / y tile
-  static constexpr int NX = NG + 1;                 // residual tile ring (one tile of prefetch)
+  // Three groups on the 128-channel block: the only way to a third tile in flight is to give up the spare
+  // residual buffer (each group then owns one x / y buffer) and to let D3 (next projection) reuse D1's TMEM
+  // columns (D1 is dead once epilogue 1 has read it): 3 x (32 + 128) = 480 of 512 columns
+  static constexpr bool ALIAS13 = !CONV && !NARROW && NG >= 3 && C == 128;
+  static constexpr int NX = ALIAS13 ? NG : NG + 1;  // residual tile ring (one tile of prefetch)
   static constexpr int NY = CONV ? 0 : NARROW ? NG : NX;   // C-wide tiles: x/y in place, or one y per group
   static constexpr int RES_RB = CRES * 2 >= 128 ? 128 : CRES * 2;   // row bytes / swizzle of a narrow residual tile
   static constexpr int RBUF = (NARROW && !CONV) ? 128 * CRES * 2 : 0;
-  static constexpr int NRING = (MINB == 1 && CI == 16) ? 18 : 9;   // conv-tap ring slots
+  static constexpr int NRING = (MINB == 1 && CI == 16) ? 18 : ALIAS13 ? 7 : 9;   // conv-tap ring slots
+  // pair-slab mode (CI = 32, two-row tiles): a slot holds one kernel row of the tile, [64 + 2 halo px][2 rows][CI]
+  // with halo <= 16: 12 KB; the same shared memory then holds NRING_PAIR slots = NRING_PAIR / 3 tiles of a 3x3 conv
+  static constexpr int PAIR_SLOT = 96 * 2 * RB;
+  static constexpr int NRING_PAIR = ALIAS13 ? 5 : NRING * SLOT_BYTES / PAIR_SLOT;
+  static constexpr int RING_BYTES = (CI == 32 && !CONV && NRING_PAIR * PAIR_SLOT > NRING * SLOT_BYTES) ? NRING_PAIR * PAIR_SLOT
+                                                                                                    : NRING * SLOT_BYTES;
   // offsets (all multiples of 1024)
   static constexpr int OFF_X = 0;
   static constexpr int OFF_R = OFF_X + NY * XBUF;
   static constexpr int OFF_TAPS = OFF_R + NX * RBUF;
-  static constexpr int OFF_E2 = ((OFF_TAPS + NRING * SLOT_BYTES + 1023) / 1024) * 1024;   // one e2 tile per group
+  static constexpr int OFF_E2 = ((OFF_TAPS + RING_BYTES + 1023) / 1024) * 1024;   // one e2 tile per group
   static constexpr int OFF_W = OFF_E2 + (CONV ? 0 : NG) * TAP_BYTES;  // weight image starts here
   static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
   static constexpr int W_LOAD = CONV ? 9 * Wt::W2_TAP : Wt::W_BYTES;  // bytes of the weight image this kernel needs
@@ -102,14 +117,15 @@ struct UmmaSmem {
   // barriers
   static constexpr int X_FULL = 0, D1_FULL = X_FULL + NX, D1_EMPTY = D1_FULL + NG,
                        E2_FULL = D1_EMPTY + NG, D2_FULL = E2_FULL + NG, Y_FULL = D2_FULL + NG, D3_FULL = Y_FULL + NG,
-                       W_FULL = D3_FULL + NG, TAP_FULL = W_FULL + 1, TAP_EMPTY = TAP_FULL + NRING,
+                       D3_EMPTY = D3_FULL + NG, W_FULL = D3_EMPTY + NG, TAP_FULL = W_FULL + 1, TAP_EMPTY = TAP_FULL + NRING,
                        NBARS = TAP_EMPTY + NRING;
   static_assert(NBARS * 8 + 8 + 4 * NX <= 1024, "barrier block");
   // 227 KB per CTA, 228 KB per SM with 1 KB reserved per resident CTA; + 1 KB alignment slack
   static_assert(TOTAL + 1024 <= 232448 && (TOTAL + 2048) * MINB <= 233472, "shared memory budget");
   // TMEM columns: every group owns a D1 / D2 / D3 accumulator
-  static constexpr uint32_t COL_D1 = 0, COL_D2 = NG * CI, COL_D3 = NG * (CI + C);
-  static constexpr uint32_t COLS_USED = CONV ? NG * CI : NG * (CI + C + CN);
+  static constexpr uint32_t COL_D1 = 0, COL_D2 = NG * CI, COL_D3 = ALIAS13 ? COL_D1 : NG * (CI + C);
+  static constexpr uint32_t COLS_USED = CONV ? NG * CI : ALIAS13 ? NG * (CI + C) : NG * (CI + C + CN);
+  static_assert(!ALIAS13 || CN == CI, "D3 reuses D1's columns");
   static constexpr uint32_t TMEM_COLS = COLS_USED <= 32 ? 32 : COLS_USED <= 64 ? 64 : COLS_USED <= 128 ? 128
                                         : COLS_USED <= 256 ? 256 : 512;
   static_assert(COLS_USED <= 512 && TMEM_COLS * MINB <= 512, "TMEM budget");
@@ -128,14 +144,14 @@ struct UmmaSmem {
 //   warps 4.. epilogue       group g = (warp - 4) / 4; one TMEM lane (= pixel) per thread:
 //                            D1 -> e2 (smem), D2 + x -> y (smem, TMA store), D3 -> e1' (global);
 //                            its first thread stores y and requests the x tile that reuses the buffer
-template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
-__global__ void __launch_bounds__(128 + 128 * NG, MINB)
+template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false, int EPW = 1>
+__global__ void __launch_bounds__(128 + 128 * NG * EPW, MINB)
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                                                                 // (narrow: [pixels][CRES], box [128 px][CRES])
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
                   const __grid_constant__ UmmaParams p) {
-  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV, EPW>;
   using Wt = UmmaWeights<C, CI, CN>;
   constexpr int RB = S::RB;
   constexpr int NX = S::NX;
@@ -157,8 +173,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     for (int i = 0; i < S::NBARS; ++i) {
       // D1_EMPTY / E2_FULL / Y_FULL: every thread of the group arrives; the rest: one arrival
       const bool by_group = (i >= S::D1_EMPTY && i < S::D1_EMPTY + NG) || (i >= S::E2_FULL && i < S::E2_FULL + NG) ||
-                            (i >= S::Y_FULL && i < S::Y_FULL + NG);
-      mbar_init(bar(i), by_group ? 128 : 1);
+                            (i >= S::Y_FULL && i < S::Y_FULL + NG) || (i >= S::D3_EMPTY && i < S::D3_EMPTY + NG);
+      mbar_init(bar(i), by_group ? 128 * EPW : 1);
     }
     for (int i = 0; i < NX; ++i) xfills[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -213,6 +229,21 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, 0, y0 - 2, n, bar(S::TAP_FULL + slot));
         slot += 3;
         if (slot == S::NRING) { slot = 0; ++round; }
+      } else if (CI == 32 && !CONV && p.pairslab) {
+        // two-row tiles of a 64-wide map: TMEM lane m is pixel (row m % 2, column m / 2) of the tile, so the A
+        // operand of kernel row ky is ONE slab [64 + 2 halo pixels][2 image rows][CI] (map_e1 lists the image row
+        // BEFORE the column, so TMA writes the two rows pixel-interleaved) and kernel column kx is the same slab
+        // read through a descriptor that starts kx * step pixels (128 bytes each) in: 3 loads of 8-12 KB per tile
+        // instead of 9 x 8 KB (1x5: one load instead of five), and the ring holds two tiles
+        const int nky = p.ntaps == 9 ? 3 : 1;
+        const uint32_t bytes = (uint32_t)(64 + 2 * p.pair_halo) * 2 * RB;
+        for (int ky = 0; ky < nky; ++ky) {
+          if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
+          mbar_expect_tx_e(bar(S::TAP_FULL + slot), bytes);
+          tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::PAIR_SLOT, &map_e1, 0, y0 + (nky == 3 ? (ky - 1) * p.pair_step : 0),
+                        -p.pair_halo, n, bar(S::TAP_FULL + slot));
+          if (++slot == S::NRING_PAIR) { slot = 0; ++round; }
+        }
       } else if (CI == 16 && p.rowslab) {
         // one-row tiles: the three taps of a kernel row are the same 130-pixel row slab read at 0 / 1 / 2 pixels
         // offset (map_e1's box is 130 pixels wide here): 3 loads and a third of the L2 -> SM bytes per tile
@@ -244,7 +275,10 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     mbar_wait(bar(S::W_FULL), 0);
     for (int k = 0; k < T; ++k) {
       const int g = k % NG;
-      if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+      if (k >= NG) {
+        mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+        if (S::ALIAS13 && p.has_next) mbar_wait(bar(S::D3_EMPTY + g), ((k / NG) - 1) & 1);   // D3 of the group's previous tile lives in D1's columns
+      }
       if (CI == 32 && p.vslab) {
         mbar_wait(bar(S::TAP_FULL + slot), round & 1);
         tc_fence_after();
@@ -257,6 +291,20 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         umma_commit_e(bar(S::TAP_EMPTY + slot));
         slot += 3;
         if (slot == S::NRING) { slot = 0; ++round; }
+      } else if (CI == 32 && !CONV && p.pairslab) {
+        const int nky = p.ntaps == 9 ? 3 : 1, nkx = p.ntaps == 9 ? 3 : 5;
+        const uint32_t dstep = (uint32_t)p.pair_step * (2 * RB >> 4);      // one pixel of the slab = two 64-byte rows
+        for (int ky = 0; ky < nky; ++ky) {
+          mbar_wait(bar(S::TAP_FULL + slot), round & 1);
+          tc_fence_after();
+          for (int kx = 0; kx < nkx; ++kx)                  // (the swizzle follows the absolute address: a whole-row shift is legal)
+#pragma unroll
+            for (int kk = 0; kk < CI / 16; ++kk)
+              umma_mma_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::PAIR_SLOT >> 4) + kx * dstep + kk * 2),
+                         dB0 + (uint64_t)((ky * nkx + kx) * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (ky | kx | kk) != 0);
+          umma_commit_e(bar(S::TAP_EMPTY + slot));
+          if (++slot == S::NRING_PAIR) { slot = 0; ++round; }
+        }
       } else if (CI == 16 && p.rowslab) {
         for (int ky = 0; ky < 3; ++ky) {
           mbar_wait(bar(S::TAP_FULL + slot), round & 1);
@@ -316,40 +364,49 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     }
   } else {
     // ============================================================ epilogue (warps 4..)
-    const int grp = (warp - 4) >> 2;         // epilogue group = tile slot
+    // EPW warps share a TMEM lane quarter of a group: warp-half eh takes 1 / EPW of the columns of every
+    // epilogue (compile-time halves, so the biases and slopes stay constant-bank operands)
+    const int grp = (warp - 4) / (4 * EPW);  // epilogue group = tile slot
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;             // row of the tile = pixel = TMEM lane
+    const int m = q * 32 + lane;             // row of the tile = TMEM lane
+    // the tile's pixel (in memory order) this lane holds: itself, or in pair-slab mode (row m % 2, column m / 2)
+    const int mp = (CI == 32 && !CONV && p.pairslab) ? ((m & 1) << 6) | (m >> 1) : m;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
-    const bool storer = ((warp & 3) == 0 && lane == 0);
     uint8_t* e2buf = smem + S::OFF_E2 + grp * S::TAP_BYTES;
     mbar_wait(bar(S::W_FULL), 0);
+    auto run = [&](auto HH) {
+    constexpr int EH = decltype(HH)::value;
+    constexpr int CI1 = CI / EPW, C1 = C / EPW, CN1 = CN / EPW;     // this warp's share of the columns
+    static_assert(CI1 % 16 == 0 && CN1 % 16 == 0 && C1 % 32 == 0, "column split");
+    const bool storer = (q == 0 && EH == 0 && lane == 0);
     for (int k = grp; k < T; k += NG) {
       const int tile = tile_of(k);
       const uint32_t par = (uint32_t)(k / NG) & 1;
-      // ---- epilogue 1: +bias, PReLU, bf16 -> e2 tile (A operand of the expansion) or global
+      // ---- epilogue 1: +bias, PReLU, 16-bit -> e2 tile (A operand of the expansion) or global
       {
-        float v[CI];
+        float v[CI1];
         mbar_wait(bar(S::D1_FULL + grp), par);
         tc_fence_after();
-        if constexpr (CI == 32) tmem_ld32(tm_lane + S::COL_D1 + grp * CI, v); else tmem_ld16(tm_lane + S::COL_D1 + grp * CI, v);
+        if constexpr (CI1 == 32) tmem_ld32(tm_lane + S::COL_D1 + grp * CI + EH * CI1, v);
+        else tmem_ld16(tm_lane + S::COL_D1 + grp * CI + EH * CI1, v);
         tc_fence_before();
         mbar_arrive(bar(S::D1_EMPTY + grp));
 #pragma unroll
-        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + p.f[F_B2 + j], p.f[F_A2 + j]);
+        for (int j = 0; j < CI1; ++j) v[j] = prelu_f(v[j] + p.f[F_B2 + EH * CI1 + j], p.f[F_A2 + EH * CI1 + j]);
         if constexpr (!full) {
-          uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI);
+          uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI + EH * CI1);
 #pragma unroll
-          for (int c = 0; c < CI / 8; ++c)
+          for (int c = 0; c < CI1 / 8; ++c)
             o[c] = pack8(v + 8 * c);
           continue;
         }
 #pragma unroll
-        for (int c = 0; c < CI / 8; ++c)
-          *reinterpret_cast<uint4*>(e2buf + swz<RB>(m * RB + c * 16)) = pack8(v + 8 * c);
+        for (int c = 0; c < CI1 / 8; ++c)
+          *reinterpret_cast<uint4*>(e2buf + swz<RB>(m * RB + (EH * CI1 / 8 + c) * 16)) = pack8(v + 8 * c);
         fence_proxy_async();
         mbar_arrive(bar(S::E2_FULL + grp));
       }
-      // ---- epilogue 2: +bias, PReLU, + residual, PReLU, bf16 -> y tile (in place over x; narrow: own buffer)
+      // ---- epilogue 2: +bias, PReLU, + residual, PReLU, 16-bit -> y tile (in place over x; narrow: own buffer)
       const int xb = k % NX;
       uint8_t* yt = smem + S::OFF_X + (NARROW ? grp : xb) * S::XBUF;
       const uint8_t* rt = smem + S::OFF_R + xb * S::RBUF;         // narrow residual tile
@@ -369,17 +426,17 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       mbar_wait(bar(S::D2_FULL + grp), par);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
+      for (int c0 = EH * C1; c0 < (EH + 1) * C1; c0 += 32) {
         float v[32];
         tmem_ld32(tm_lane + S::COL_D2 + grp * C + c0, v);
         uint8_t* yrow = yt + (c0 / 64) * S::XSUB;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 channels
           const int ch = c0 + 8 * c;
-          uint4* py = reinterpret_cast<uint4*>(yrow + swz<128>(m * 128 + ((ch % 64) / 8) * 16));
+          uint4* py = reinterpret_cast<uint4*>(yrow + swz<128>(mp * 128 + ((ch % 64) / 8) * 16));
           uint4 xr = make_uint4(0u, 0u, 0u, 0u);      // channels beyond CRES: zero padding of the main branch
           if constexpr (!NARROW) xr = *py;
-          else if (ch < CRES) xr = *reinterpret_cast<const uint4*>(rt + swz<S::RES_RB>(m * S::RES_RB + (ch / 8) * 16));
+          else if (ch < CRES) xr = *reinterpret_cast<const uint4*>(rt + swz<S::RES_RB>(mp * S::RES_RB + (ch / 8) * 16));
           const uint32_t* xh = reinterpret_cast<const uint32_t*>(&xr);
           float o[8];
 #pragma unroll
@@ -411,18 +468,20 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           }
         }
       }
-      // ---- epilogue 3: the next block's projection: +bias, PReLU, bf16 -> e1' (global)
+      // ---- epilogue 3: the next block's projection: +bias, PReLU, 16-bit -> e1' (global)
       if (p.has_next) {
         mbar_wait(bar(S::D3_FULL + grp), par);
         tc_fence_after();
-        float v[CN];
-        if constexpr (CN == 32) tmem_ld32(tm_lane + S::COL_D3 + grp * CN, v); else tmem_ld16(tm_lane + S::COL_D3 + grp * CN, v);
+        float v[CN1];
+        if constexpr (CN1 == 32) tmem_ld32(tm_lane + S::COL_D3 + grp * CN + EH * CN1, v);
+        else tmem_ld16(tm_lane + S::COL_D3 + grp * CN + EH * CN1, v);
         tc_fence_before();
+        if constexpr (S::ALIAS13) mbar_arrive(bar(S::D3_EMPTY + grp));
 #pragma unroll
-        for (int j = 0; j < CN; ++j) v[j] = prelu_f(v[j] + p.f[F_B1N + j], p.f[F_A1N + j]);
-        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CN);
+        for (int j = 0; j < CN1; ++j) v[j] = prelu_f(v[j] + p.f[F_B1N + EH * CN1 + j], p.f[F_A1N + EH * CN1 + j]);
+        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CN + EH * CN1);
 #pragma unroll
-        for (int c = 0; c < CN / 8; ++c)
+        for (int c = 0; c < CN1 / 8; ++c)
           o[c] = pack8(v + 8 * c);
       }
       // The y buffer may be overwritten once the store has read it (and the projection MMAs, which
@@ -441,9 +500,15 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           }
         }
       }
-      if constexpr (NARROW) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if constexpr (NARROW) asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(128 * EPW) : "memory");
     }
     if (storer) tma_store_wait_all();
+    };
+    if constexpr (EPW == 1) {
+      run(std::integral_constant<int, 0>{});
+    } else {
+      if (((warp - 4) >> 2) % EPW == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
+    }
   }
   // ---- teardown
   tc_fence_before();
@@ -495,6 +560,18 @@ bool make_map_box(CUtensorMap* m, const act_t* base, int N, int H, int W, int CI
   cuuint64_t dims[4] = {(cuuint64_t)CI, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)CI * 2, (cuuint64_t)W * CI * 2, (cuuint64_t)H * W * CI * 2};
   cuuint32_t box[4] = {(cuuint32_t)CI, (cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, ACT_TMAP, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swizzle_for(CI * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// pair-slab view of a [N][H][W][CI] tensor: dims (CI, y, x, n) -- the image row BEFORE the column -- and box
+// [1][box_x][2][CI], so that TMA writes two image rows pixel-interleaved: smem [x][row][CI]
+bool make_map_pair(CUtensorMap* m, const act_t* base, int N, int H, int W, int CI, int box_x) {
+  PFN_encodeTiled enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)CI, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)W * CI * 2, (cuuint64_t)CI * 2, (cuuint64_t)H * W * CI * 2};
+  cuuint32_t box[4] = {(cuuint32_t)CI, 2, (cuuint32_t)box_x, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(m, ACT_TMAP, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swizzle_for(CI * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -583,20 +660,33 @@ static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* 
   return true;
 }
 
-template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false>
+template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false, int EPW = 1>
 static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
-  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV, EPW>;
   CUtensorMap me1, mx, my;
   // row-slab mode: a plain 3x3 conv (dilation 1, taps in row-major order) whose 128-pixel tile is one image row
-  static const bool no_rowslab = getenv("BC_NO_ROWSLAB") != nullptr, no_vslab = getenv("BC_NO_VSLAB") != nullptr;   // read once
+  static const bool no_rowslab = getenv("BC_NO_ROWSLAB") != nullptr, no_vslab = getenv("BC_NO_VSLAB") != nullptr,
+                    no_pairslab = getenv("BC_NO_PAIRSLAB") != nullptr;   // read once
+  // pair-slab mode: a 3x3 conv (one dilation for both axes, taps in row-major order) or a 1x5 conv on two-row tiles
+  int pair_step = 0, pair_halo = 0;
+  bool pairslab = CI == 32 && !CONV && W == 64 && H % 2 == 0 && !no_pairslab && (ntaps == 9 || ntaps == 5);
+  if (pairslab && ntaps == 9) {
+    pair_step = pair_halo = taps.dx[8];
+    pairslab = pair_step >= 1 && pair_step <= 16;
+    for (int t = 0; pairslab && t < 9; ++t) pairslab = taps.dy[t] == (t / 3 - 1) * pair_step && taps.dx[t] == (t % 3 - 1) * pair_step;
+  } else if (pairslab) {
+    pair_step = 1; pair_halo = 2;
+    for (int t = 0; pairslab && t < 5; ++t) pairslab = taps.dy[t] == 0 && taps.dx[t] == t - 2;
+  }
   bool rowslab = CI == 16 && !CONV && ntaps == 9 && W == 128 && !no_rowslab;
   for (int t = 0; rowslab && t < 9; ++t) rowslab = taps.dy[t] == t / 3 - 1 && taps.dx[t] == t % 3 - 1;
   // vertical-slab mode: a 5x1 conv (taps dy = -2..2, dx = 0) whose tile is two full-width rows of 64 pixels
   bool vslab = CI == 32 && S::NRING == 9 && ntaps == 5 && W == 64 && !no_vslab;
   for (int t = 0; vslab && t < 5; ++t) vslab = taps.dy[t] == t - 2 && taps.dx[t] == 0;
-  if (rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1)
-              : vslab ? !make_map_box(&me1, e1, n, H, W, CI, 64, 6) : !make_map_e1(&me1, e1, n, H, W, CI))
+  if (pairslab ? !make_map_pair(&me1, e1, n, H, W, CI, 64 + 2 * pair_halo)
+      : rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1)
+      : vslab ? !make_map_box(&me1, e1, n, H, W, CI, 64, 6) : !make_map_e1(&me1, e1, n, H, W, CI))
     return cudaErrorInvalidValue;
   size_t px = (size_t)n * H * W;
   if (S::NARROW) {
@@ -616,6 +706,9 @@ static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* 
   if ((conv_only != 0) != CONV) return cudaErrorInvalidValue;
   p.rowslab = rowslab ? 1 : 0;
   p.vslab = vslab ? 1 : 0;
+  p.pairslab = pairslab ? 1 : 0;
+  p.pair_step = pair_step;
+  p.pair_halo = pair_halo;
   p.reverse = g_umma_reverse;
   p.has_next = has_next;
   p.out_small = out_small;
@@ -624,7 +717,7 @@ static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* 
   const int smem = S::TOTAL + 1024;        // opt-in set per device by prepare_bottleneck()
   const int ctas = num_sms * MINB;
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
+  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }
 
@@ -642,15 +735,16 @@ bool Umma<act_t>::available() { return encode_fn() != nullptr; }
 
 // the kernel configurations launch() can select (one opt-in per instantiation and device)
 #define BC_UMMA_CONFIGS(X) \
-  X(128, 32, 32, 128, 2, 2, true) X(128, 32, 32, 128, 2, 1, false) X(64, 16, 16, 64, 1, 2, false) \
-  X(64, 16, 16, 64, 2, 2, false) X(64, 16, 16, 64, 4, 1, false) X(64, 16, 16, 16, 2, 2, false) X(128, 16, 32, 64, 2, 1, false)
+  X(128, 32, 32, 128, 2, 2, true, 1) X(128, 32, 32, 128, 2, 1, false, 1) X(128, 32, 32, 128, 3, 1, false, 1) \
+  X(128, 32, 32, 128, 2, 1, false, 2) X(64, 16, 16, 64, 1, 2, false, 1) X(64, 16, 16, 64, 2, 2, false, 1) \
+  X(64, 16, 16, 64, 4, 1, false, 1) X(64, 16, 16, 16, 2, 2, false, 1) X(128, 16, 32, 64, 2, 1, false, 1)
 
 cudaError_t Umma<act_t>::prepare_bottleneck() {
   cudaError_t e = cudaSuccess;
-#define BC_SET(C_, CI_, CN_, CR_, NG_, MB_, CV_)                                                              \
+#define BC_SET(C_, CI_, CN_, CR_, NG_, MB_, CV_, EP_)                                                         \
   if (e == cudaSuccess)                                                                                        \
-    e = cudaFuncSetAttribute(k_umma_bottleneck<C_, CI_, CN_, CR_, NG_, MB_, CV_>,                              \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<C_, CI_, CN_, CR_, NG_, MB_, CV_>::TOTAL + 1024);
+    e = cudaFuncSetAttribute(k_umma_bottleneck<C_, CI_, CN_, CR_, NG_, MB_, CV_, EP_>,                         \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<C_, CI_, CN_, CR_, NG_, MB_, CV_, EP_>::TOTAL + 1024);
   BC_UMMA_CONFIGS(BC_SET)
 #undef BC_SET
   return e;
@@ -675,12 +769,17 @@ bool Umma<act_t>::build(UmmaPack& out, int C, int CI, int CN, int CRES, const fl
 cudaError_t Umma<act_t>::launch(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,
                                 int W, const Taps& taps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
   if (128 % W != 0 && W % 128 != 0) return cudaErrorInvalidValue;
-  static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 41);
+  static const int cfg64 = cfg_from_env("BC_UMMA_CFG64", 41), cfg128 = cfg_from_env("BC_UMMA_CFG128", 21);
 #define BC_LAUNCH(C_, CI_, CN_, CR_, NG_, MB_) \
   return launch_one<C_, CI_, CN_, CR_, NG_, MB_>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, conv_only, has_next, num_sms, s)
   if (pk.C == 128 && pk.CI == 32 && pk.CRES == 128) {
     if (conv_only)
       return launch_one<128, 32, 32, 128, 2, 2, true>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, 1, 0, num_sms, s);
+    // three groups (D3 over D1's TMEM columns, one x / y buffer per group, no spare) measured SLOWER than two
+    // groups with a spare residual buffer: 70.8 vs 65.8 us per launch; kept selectable for A/B runs
+    if (cfg128 == 31) BC_LAUNCH(128, 32, 32, 128, 3, 1);
+    if (cfg128 == 22)       // two warps per TMEM lane quarter: every epilogue of a tile is split over 8 warps
+      return launch_one<128, 32, 32, 128, 2, 1, false, 2>(pk, e1, x, y, out_small, n, H, W, taps, pk.ntaps, 0, has_next, num_sms, s);
     BC_LAUNCH(128, 32, 32, 128, 2, 1);
   }
   if (pk.C == 64 && pk.CI == 16 && pk.CRES == 64) {

@@ -13,6 +13,9 @@
 // restated (and pinned against cv2) in oracle/cv_ops.py.
 #include "internal.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace bc {
 
 static constexpr int NET_W = 512, NET_H = 256;
@@ -197,24 +200,30 @@ __device__ __forceinline__ int occ_sample(const uint8_t* __restrict__ lab, uint4
   const uint8_t* p0 = lab + e.x;
   const uint8_t* p1 = p0 + ((e.w & 2) ? cols : 0);
   const unsigned dx = e.w & 1;
-  unsigned acc = ((p0[0] + 1u) & 255u) * (e.y & 0xffffu) + ((p0[dx] + 1u) & 255u) * (e.y >> 16) +
-                 ((p1[0] + 1u) & 255u) * (e.z & 0xffffu) + ((p1[dx] + 1u) & 255u) * (e.z >> 16);
-  return (int)((acc + 512u) >> 10);
+  // the four taps as bytes of one word, +1 per byte with uint8 wrap-around, then two 2-way dot products of
+  // 16-bit weights x bytes (dp2a): same integers as the scalar form, a third fewer instructions
+  const unsigned top = (unsigned)p0[0] | ((unsigned)p0[dx] << 8), bot = (unsigned)p1[0] | ((unsigned)p1[dx] << 8);
+  const unsigned px = __vadd4(top | (bot << 16), 0x01010101u);
+  unsigned acc = __dp2a_lo(e.y, px, 512u);        // w00 * byte 0 + w01 * byte 1
+  acc = __dp2a_hi(e.z, px, acc);                  // w10 * byte 2 + w11 * byte 3
+  return (int)(acc >> 10);
 }
 
 __device__ __forceinline__ bool is_occ(int v, int binary) {
   return binary ? (v == 1) : (v == 1 || v == 3);   // bev.py:128 / bev.py:196
 }
 
-// One thread per grid cell, OCC_FRAMES frames per block (the block's slice of the table is
-// staged in shared memory once and reused for every frame).  The cell takes template pixel
+// One thread per grid cell, `fpb` frames per block (the block's slice of the table is staged in
+// shared memory once and reused for every frame).  Blocks stay small (8 frames): the cost of a cell
+// depends on the scene (occupied cells sample up to 25 template pixels, free ones a single one), so
+// many short blocks balance themselves over the SMs; one resident wave of 37-frame blocks measured
+// 129 us against 105 us (the slowest block sets the time).  The cell takes template pixel
 // (ty, tx) (nearest resize); if that pixel is "occupied" the 3x3 opening decides whether it
 // is a speck:
 //   opened(p) = OR_{q in N3(p)} AND_{r in N3(q)} occ(r)   (erode ignores pixels outside
 //   the template, dilate treats them as 0 -- OpenCV default border values)
 // evaluated lazily: q = p needs only the inner 3x3 ring; the outer ring of the 5x5 block is
 // sampled only when that fails (the interior of an occupied region never gets there).
-static constexpr int OCC_FRAMES = 8;
 static constexpr unsigned OCC_INNER = (7u << 6) | (7u << 11) | (7u << 16);     // 3x3 block around bit 12
 
 // outer ring of the 5x5 block, k = 0..15 -> bit position
@@ -223,7 +232,7 @@ __device__ __forceinline__ int occ_outer_pos(int k) {
 }
 
 __global__ void __launch_bounds__(128)
-k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __restrict__ grids) {
+k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int fpb, int8_t* __restrict__ grids) {
   extern __shared__ uint4 tab[];                  // [25][128]
   const uint4* __restrict__ table = g.table;
   const int cells = g.Hc * g.Wc;
@@ -243,7 +252,7 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
   const size_t o = g.ros_layout ? (size_t)(g.Wc - 1 - cx) * g.Hc + (g.Hc - 1 - cy)   // occgrid_to_ros.py:18-21
                                 : (size_t)cell;
   const int rows = g.in_rows, cols = g.in_cols;
-  const int n1 = min(B, (int)(blockIdx.y + 1) * OCC_FRAMES);
+  const int n1 = min(B, (int)(blockIdx.y + 1) * fpb);
   // what this lane does when it helps with another lane's outer ring / opening test
   const int my_outer = occ_outer_pos(k16);
   unsigned my_q = 0, my_nb = 0;                    // lanes 0..8 of each half: one erosion centre q each
@@ -253,7 +262,7 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int8_t* __
     for (int rj = -1; rj <= 1; ++rj)
       for (int ri = -1; ri <= 1; ++ri) my_nb |= 1u << ((qj + rj) * 5 + (qi + ri));
   }
-  for (int n = blockIdx.y * OCC_FRAMES; n < n1; ++n) {
+  for (int n = blockIdx.y * fpb; n < n1; ++n) {
     const uint8_t* lab = labels + (size_t)n * rows * cols;
     int v = occ_sample(lab, tab[12 * 128 + threadIdx.x], cols);
     const bool occupied = live && is_occ(v, g.binary);
@@ -314,8 +323,11 @@ cudaError_t prepare_occgrid() { return cudaFuncSetAttribute(k_occgrid, cudaFuncA
 
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s) {
   const int smem = OCC_SMEM;
-  dim3 grid((g.Hc * g.Wc + 127) / 128, (B + OCC_FRAMES - 1) / OCC_FRAMES);
-  k_occgrid<<<grid, 128, smem, s>>>(labels, g, B, grids);
+  static const int fpb_env = getenv("BC_OCC_FPB") ? atoi(getenv("BC_OCC_FPB")) : 0;     // tuning knob, read once
+  const int fpb = fpb_env > 0 ? fpb_env : 8;
+  const int cell_blocks = (g.Hc * g.Wc + 127) / 128;
+  dim3 grid(cell_blocks, (B + fpb - 1) / fpb);
+  k_occgrid<<<grid, 128, smem, s>>>(labels, g, B, fpb, grids);
 }
 
 }  // namespace bc

@@ -16,6 +16,7 @@
 // accumulator are double buffered.
 #include "umma_common.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace bc {
@@ -40,10 +41,35 @@ static constexpr int HEAD_OFF_LUT = HEAD_OFF_W + 4 * HEAD_WTAP;
 static constexpr int HEAD_OFF_BAR = HEAD_OFF_LUT + 256;
 static constexpr int HEAD_SMEM = HEAD_OFF_BAR + 128;
 
+// The label of a pixel is lut[argmax_c logit_c].  For the reference's two class groupings over the 15 classes of
+// note_label (models.py:56-58 three-way, models.py:79-80 binary) only the GROUP of the winning class matters, so
+// the epilogue takes the maximum per group (3-input fmax trees, no index bookkeeping) and compares the group
+// maxima: 12 instead of 45 instructions per output pixel.  tf.math.argmax returns the LOWEST index among equal
+// maxima (models.py:55): classes 0 and 1 (road) win every tie; a tie between the flat group {2, 9} and the rest
+// depends on which classes attain it, so that (measure-zero) case takes the exact index scan.
+enum { HEAD_LUT_GENERIC = 0, HEAD_LUT_3WAY = 1, HEAD_LUT_BINARY = 2 };
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// exact scan: first maximum wins
+template <int CT>
+__device__ __forceinline__ int argmax_first(const float* v, int C) {
+  float best = v[0];
+  int bi = 0;
+#pragma unroll
+  for (int c = 1; c < 16; ++c)
+    if (c < (CT ? CT : C) && v[c] > best) { best = v[c]; bi = c; }
+  return bi;
+}
+
 // 44 KB of shared memory and 128 TMEM columns per CTA: four CTAs per SM keep four tiles in flight
 // CT: the class count as a compile-time constant (0 = read it from the parameters): the argmax loop then carries
-// no per-class range predicate
-template <int CT>
+// no per-class range predicate.  MODE: HEAD_LUT_* (the grouped forms need CT == 15)
+template <int CT, int MODE = HEAD_LUT_GENERIC>
 __global__ void __launch_bounds__(192, 4)
 k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16], box [1][1][129][16], 32-byte swizzle
             const HeadParams p) {
@@ -125,12 +151,24 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float* v = q < 2 ? v0 + 16 * q : v1 + 16 * (q - 2);
-        float best = v[0];
-        int bi = 0;
-#pragma unroll
-        for (int c = 1; c < 16; ++c)
-          if (c < C && v[c] > best) { best = v[c]; bi = c; }      // first maximum wins (models.py:55)
-        lab[q] = slut[bi];
+        if constexpr (MODE == HEAD_LUT_GENERIC) {
+          lab[q] = slut[argmax_first<CT>(v, C)];                   // first maximum wins (models.py:55)
+        } else {
+          static_assert(MODE == HEAD_LUT_GENERIC || CT == 15, "grouped argmax is written for the 15 classes of note_label");
+          const float road = fmaxf(v[0], v[1]);
+          if constexpr (MODE == HEAD_LUT_BINARY) {                 // models.py:79-80: 1 iff the winner is class 0 or 1
+            const float other = fmaxf(fmax3(fmax3(v[2], v[3], v[4]), fmax3(v[5], v[6], v[7]), fmax3(v[8], v[9], v[10])),
+                                      fmax3(v[11], v[12], fmaxf(v[13], v[14])));
+            lab[q] = road >= other ? 1 : 0;                        // classes 0, 1 have the lowest indices: they win ties
+          } else {                                                 // models.py:56-58: {0,1} -> 1, {2,9} -> 0, rest -> 2
+            const float flat = fmaxf(v[2], v[9]);
+            const float rest = fmaxf(fmax3(fmax3(v[3], v[4], v[5]), fmax3(v[6], v[7], v[8]), fmax3(v[10], v[11], v[12])),
+                                     fmaxf(v[13], v[14]));
+            int l = road >= fmaxf(flat, rest) ? 1 : flat > rest ? 0 : 2;
+            if (flat == rest && road < flat) l = slut[argmax_first<CT>(v, C)];   // tie between the groups: exact scan
+            lab[q] = (uint8_t)l;
+          }
+        }
       }
       uint8_t* o = p.labels + ((size_t)(n * 256 + 2 * y) * 512 + 2 * x);
       *reinterpret_cast<uchar2*>(o) = make_uchar2(lab[0], lab[1]);
@@ -178,6 +216,8 @@ cudaError_t Umma<act_t>::prepare_head() {
   cudaError_t e = cudaFuncSetAttribute(k_umma_head<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<15, HEAD_LUT_3WAY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_umma_head<15, HEAD_LUT_BINARY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   return e;
 }
 
@@ -194,7 +234,20 @@ cudaError_t Umma<act_t>::launch_head(const act_t* x, int B, int C, const uint8_t
   p.lut = lut;
   const int smem = HEAD_SMEM + 1024;       // opt-in set per device by prepare_head()
   int grid = p.num_tiles < 4 * num_sms ? p.num_tiles : 4 * num_sms;
-  if (C == 15) k_umma_head<15><<<grid, 192, smem, s>>>(mx, p);          // note_label:1-15
+  // the reference's own class groupings take the grouped epilogue (any other LUT: the generic index scan)
+  int mode = HEAD_LUT_GENERIC;
+  if (C == 15) {
+    bool three = true, two = true;
+    for (int c = 0; c < 15; ++c) {
+      three = three && lut.v[c] == (c <= 1 ? 1 : (c == 2 || c == 9) ? 0 : 2);
+      two = two && lut.v[c] == (c <= 1 ? 1 : 0);
+    }
+    static const bool no_group = getenv("BC_NO_HEAD_GROUPS") != nullptr;
+    mode = no_group ? HEAD_LUT_GENERIC : three ? HEAD_LUT_3WAY : two ? HEAD_LUT_BINARY : HEAD_LUT_GENERIC;
+  }
+  if (mode == HEAD_LUT_3WAY) k_umma_head<15, HEAD_LUT_3WAY><<<grid, 192, smem, s>>>(mx, p);
+  else if (mode == HEAD_LUT_BINARY) k_umma_head<15, HEAD_LUT_BINARY><<<grid, 192, smem, s>>>(mx, p);
+  else if (C == 15) k_umma_head<15><<<grid, 192, smem, s>>>(mx, p);     // note_label:1-15
   else if (C == 16) k_umma_head<16><<<grid, 192, smem, s>>>(mx, p);
   else k_umma_head<0><<<grid, 192, smem, s>>>(mx, p);
   return cudaGetLastError();

@@ -28,6 +28,8 @@ struct InitParams {
   const uint8_t* wblob;      // [hi | lo][16 rows][32 k] tf32 (fp32 bit patterns), 128-byte swizzled rows
   const float* lut;          // [256][3] fp32 normalisation table (RGB order)
   float f[48];               // BN scale g[16], shift b[16], PReLU slope a[16]
+  float fu8[16];             // uint8 kernel: g[o] * 2^-e(o), the un-scale of its fp16 weight limbs folded in
+  float fpool[6];            // uint8 kernel, pooled channels: byte -> BN(normalise(byte)) = byte * fpool[c] + fpool[3 + c]
 };
 
 static constexpr int INIT_A = 128 * 128;          // one A tile: 128 rows x 32 tf32
@@ -190,16 +192,36 @@ k_umma_initial(const __grid_constant__ InitParams p) {
 // t_c = -mean_c / std_c (models.py:17-18,91), so
 //     sum_k w_k v_k = sum_k (w_k s_c) u_k + sum_taps valid(tap) * (sum_c w_(c,tap) t_c)
 // where valid(tap) = 0 for taps in the zero padding (the conv pads the NORMALISED image).  The A
-// operand is then the RAW bytes (exact in bf16) plus nine 0/1 validity columns: no lookup table, no
-// fp32 operand split on the activation side (4x less shared-memory traffic than the tf32 form);
-// the folded weights carry their full fp32 precision as three bf16 limbs.  K = 27 + 9, padded to 64.
-static constexpr int U8_A = 128 * 128;            // A tile: 128 rows x 64 bf16
-static constexpr int U8_W = 16 * 128;             // one limb of B: 16 rows x 64 bf16
-static constexpr int U8_OFF_A = 0;
-static constexpr int U8_OFF_W = U8_A;
+// operand is then the RAW bytes (exact in fp16) plus nine 0/1 validity columns: no lookup table, no
+// fp32 operand split on the activation side.  The 27 window bytes of an output pixel arrive as nine
+// aligned 32-bit words; a byte pair becomes two fp16 values with ONE byte permute (0x64 above each
+// byte: 0x64bb is the fp16 number 1024 + bb) and ONE packed subtraction of 1024 -- no integer-to-float
+// conversions, no per-byte extraction; the 3-channel max-pool is a packed byte maximum on the same
+// words.  K order (any order is legal as long as B uses the same): per window row ky the bytes
+// 0..7 (8 halves), then the three bytes 8, then the validity flags; K = 40, padded to 48.
+// The folded weights keep fp32 accuracy as three fp16 limbs of  w_k s_c 2^e(o)  with a per-output-
+// channel power of two e(o) that lifts the row into fp16's normal range; 2^-e(o) is folded into the
+// batch-norm scale of the epilogue.
+static constexpr int U8_A = 128 * 128;            // A tile: 128 rows x 64 fp16 (48 used)
+static constexpr int U8_W = 16 * 128;             // one limb of B: 16 rows x 64 fp16
+static constexpr int U8_K = 48;
+static constexpr int U8_OFF_A = 0;                // two A tiles: tile k+1 is built while the MMAs of tile k run
+static constexpr int U8_OFF_W = 2 * U8_A;
 static constexpr int U8_OFF_BAR = U8_OFF_W + 3 * U8_W;
 static constexpr int U8_SMEM = U8_OFF_BAR + 64;
-static constexpr int U8_MINB = 7;
+static constexpr int U8_MINB = 5;
+
+// K index of window byte b (0..8) of row ky, and of the validity flag of tap (ky, kx)
+__host__ __device__ constexpr int u8_k_byte(int ky, int b) { return b < 8 ? ky * 8 + b : 24 + ky; }
+__host__ __device__ constexpr int u8_k_valid(int ky, int kx) { return 28 + ky * 3 + kx; }
+
+// bytes i and j of `w` as the fp16 pair (i in the low half)
+template <int I, int J>
+__device__ __forceinline__ uint32_t bytes_to_h2(uint32_t w) {
+  const uint32_t biased = __byte_perm(w, 0x64646464u, (4u << 12) | ((uint32_t)J << 8) | (4u << 4) | (uint32_t)I);   // 1024 + byte
+  const __half2 r = __hsub2(*reinterpret_cast<const __half2*>(&biased), __half2(__ushort_as_half(0x6400), __ushort_as_half(0x6400)));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 __global__ void __launch_bounds__(160, U8_MINB)
 k_umma_initial_u8(const __grid_constant__ InitParams p) {
@@ -207,14 +229,16 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + U8_OFF_BAR);
-  enum { A_FULL = 0, D_FULL, W_FULL, NBARS };
+  enum { A_FULL0 = 0, A_FULL1, D_FULL0, D_FULL1, W_FULL, NBARS };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    mbar_init(bar(A_FULL), 128);
-    mbar_init(bar(D_FULL), 1);
+    mbar_init(bar(A_FULL0), 128);
+    mbar_init(bar(A_FULL1), 128);
+    mbar_init(bar(D_FULL0), 1);
+    mbar_init(bar(D_FULL1), 1);
     mbar_init(bar(W_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar(W_FULL), 3 * U8_W);
@@ -224,11 +248,13 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   } else {
-    // K columns 40..63 of this thread's A row are never written again: zero them once
+    // K columns 40..63 of this thread's A rows are never written again: zero them once
     const int m = (warp & 3) * 32 + lane;
 #pragma unroll
-    for (int j = 5; j < 8; ++j)
-      *reinterpret_cast<uint4*>(smem + U8_OFF_A + swz<128>((uint32_t)(m * 128 + j * 16))) = make_uint4(0u, 0u, 0u, 0u);
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int j = 5; j < 8; ++j)
+        *reinterpret_cast<uint4*>(smem + U8_OFF_A + b * U8_A + swz<128>((uint32_t)(m * 128 + j * 16))) = make_uint4(0u, 0u, 0u, 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -239,17 +265,20 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
 
   if (warp == 0) {
     const uint64_t dA0 = smem_desc<128>(sbase + U8_OFF_A), dB0 = smem_desc<128>(sbase + U8_OFF_W);
+    constexpr uint32_t IDESC = instr_desc_fmt(128, 16, 0u);       // fp16 bytes x fp16 weight limbs, whatever act_t is
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
-      mbar_wait(bar(A_FULL), k & 1);
+      const int b = k & 1;
+      // A_FULL(k) also says that accumulator b is free: every thread read tile k-2's result before it built tile k
+      mbar_wait(bar(A_FULL0 + b), (k >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int limb = 0; limb < 3; ++limb)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_mma_e(tmem, dA0 + (uint64_t)(kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2),
-                     instr_desc_fmt(128, 16, 1u), (limb | kk) != 0);   // bytes and weight limbs are bf16 whatever act_t is
-      umma_commit_e(bar(D_FULL));
+        for (int kk = 0; kk < U8_K / 16; ++kk)
+          umma_mma_e(tmem + b * 16, dA0 + (uint64_t)(b * (U8_A >> 4) + kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2),
+                     IDESC, (limb | kk) != 0);
+      umma_commit_e(bar(D_FULL0 + b));
     }
   } else {
     const int q4 = warp & 3;
@@ -258,8 +287,10 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     // The 3 x 3 pixel window of an output pixel is 9 contiguous bytes per input row, starting at byte
     // 6*ox - 3 of the row: fetched as the three aligned 32-bit words that cover them, realigned with
     // funnel shifts.  ox = 0: the first word would lie before the row; its bytes are padding anyway.
-    // The words of tile k+1 are requested before this thread waits for tile k's accumulator, so the
-    // global-load latency hides behind the MMA round trip.
+    // Words of rows outside the image stay zero, so every padding tap is a zero byte.
+    // Software pipeline per thread: the words of tile k+2 are requested, then the A row of tile k+1 is built
+    // (second A buffer) and handed to the MMA warp, and only then does the thread wait for tile k's
+    // accumulator: global-load latency and the MMA round trip both hide behind useful work.
     uint32_t w[9];
     int pix = 0, ox = 0, oy = 0;
     auto fetch = [&](int k) {
@@ -280,65 +311,64 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
         }
       }
     };
-    if (T > 0) fetch(0);
-    for (int k = 0; k < T; ++k) {
-      // ---- A row: bf16 halves, column (c*3 + ky)*3 + kx = byte of RGB channel c, column 27 + ky*3 + kx = valid
-      uint32_t h[40];                                   // one bf16 per entry (low 16 bits), packed below
-#pragma unroll
-      for (int i = 36; i < 40; ++i) h[i] = 0u;
-      uint32_t mxb[3] = {0u, 0u, 0u};
+    // builds the A row of the tile whose words are in w[] into buffer b; returns the packed max-pool bytes (B, G, R)
+    auto build = [&](int b) -> uint32_t {
+      uint8_t* A = smem + U8_OFF_A + b * U8_A;
       const int sh = ((6 * ox - 3) & 3) * 8;            // 8 or 24
+      uint32_t r2[3], mx4 = 0u;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        const int iy = 2 * oy - 1 + ky;
-        const bool rok = iy >= 0 && iy < IH;
-        const uint32_t r0 = __funnelshift_r(w[3 * ky], w[3 * ky + 1], sh), r1 = __funnelshift_r(w[3 * ky + 1], w[3 * ky + 2], sh),
-                       r2 = w[3 * ky + 2] >> sh;        // window bytes 0-3, 4-7, 8
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const bool ok = rok && (kx > 0 || ox > 0);    // the window never leaves the row on the right (ix <= 511)
-          uint32_t u[3];                                // RGB from the BGR bytes 3*kx + (2, 1, 0)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int bi = 3 * kx + 2 - c;
-            const uint32_t word = bi < 4 ? r0 : bi < 8 ? r1 : r2;
-            u[c] = ok ? (word >> (8 * (bi & 3))) & 0xffu : 0u;
-          }
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            mxb[c] = max(mxb[c], u[c]);                                        // valid taps only (others are 0)
-            h[(c * 3 + ky) * 3 + kx] = __float_as_uint((float)u[c]) >> 16;     // exact: u < 256
-          }
-          h[27 + ky * 3 + kx] = ok ? 0x3f80u : 0u;                             // 1.0 / 0.0
-        }
+        // window bytes 0-3, 4-7, 8 (B G R of the three pixels, in memory order)
+        const uint32_t r0 = __funnelshift_r(w[3 * ky], w[3 * ky + 1], sh), r1 = __funnelshift_r(w[3 * ky + 1], w[3 * ky + 2], sh);
+        r2[ky] = (w[3 * ky + 2] >> sh) & 0xffu;
+        *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + ky * 16))) =
+            make_uint4(bytes_to_h2<0, 1>(r0), bytes_to_h2<2, 3>(r0), bytes_to_h2<0, 1>(r1), bytes_to_h2<2, 3>(r1));
+        // max-pool: bytes 0-2 of (r0, the window from byte 3, the window from byte 6) are the three pixels' B G R
+        const uint32_t p1 = __funnelshift_r(r0, r1, 24), p2 = __funnelshift_r(r1, r2[ky], 16);
+        mx4 = __vmaxu4(mx4, __vmaxu4(r0, __vmaxu4(p1, p2)));
       }
-      // (the previous tile's MMAs have finished reading A: this thread passed its D_FULL wait below)
-#pragma unroll
-      for (int j = 0; j < 5; ++j)
-        *reinterpret_cast<uint4*>(smem + U8_OFF_A + swz<128>((uint32_t)(m * 128 + j * 16))) =
-            make_uint4(h[8 * j] | (h[8 * j + 1] << 16), h[8 * j + 2] | (h[8 * j + 3] << 16),
-                       h[8 * j + 4] | (h[8 * j + 5] << 16), h[8 * j + 6] | (h[8 * j + 7] << 16));
+      // bytes 8 of the three rows, then the validity flags (1.0 = 0x3c00): only the first row / column of the
+      // image has taps in the padding (2*oy + 1 <= 255 and 2*ox + 1 <= 511 always are inside)
+      const uint32_t vt = oy > 0 ? 0x3c00u : 0u, vl = ox > 0 ? 0x3c00u : 0u, vtl = (oy > 0 && ox > 0) ? 0x3c00u : 0u;
+      const uint32_t b8a = bytes_to_h2<0, 2>(r2[0] | (r2[1] << 16)), b8b = bytes_to_h2<0, 1>(r2[2]) & 0xffffu;
+      *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 3 * 16))) = make_uint4(b8a, b8b, vtl | (vt << 16), vt | (vl << 16));
+      *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 4 * 16))) = make_uint4(0x3c003c00u, vl | (0x3c00u << 16), 0x3c00u, 0u);
       fence_proxy_async();
-      mbar_arrive(bar(A_FULL));
-      // max-pool of the normalised image = normalisation of the max byte (the map is increasing)
-      float mx[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) mx[c] = __ldg(p.lut + mxb[c] * 3 + c);
-      const int out_pix = pix;
-      if (k + 1 < T) fetch(k + 1);
-      // ---- epilogue: BN + PReLU on the 13 conv channels and the 3 pooled ones
-      mbar_wait(bar(D_FULL), k & 1);
+      mbar_arrive(bar(A_FULL0 + b));
+      return mx4;
+    };
+    uint32_t mx_cur = 0u, mx_next = 0u;
+    int pix_cur = 0, pix_next = 0;
+    if (T > 0) {
+      fetch(0);
+      pix_cur = pix;
+      mx_cur = build(0);
+      if (T > 1) fetch(1);
+    }
+    for (int k = 0; k < T; ++k) {
+      if (k + 1 < T) {                                  // tile k+1: its words arrived while tile k-1 was finished
+        pix_next = pix;
+        mx_next = build((k + 1) & 1);                   // (the MMAs of tile k-1 have finished reading that buffer: D_FULL(k-1) was waited for)
+        if (k + 2 < T) fetch(k + 2);
+      }
+      // ---- epilogue of tile k: BN (with the weights' power-of-two un-scale folded in) + PReLU on the 13 conv
+      // channels; the 3 pooled channels: max-pool of the normalised image = normalisation of the max byte (the
+      // map is increasing), and normalisation + BN are one affine map of the byte (host-folded, fpool)
+      mbar_wait(bar(D_FULL0 + (k & 1)), (k >> 1) & 1);
       tc_fence_after();
       float r[16];
-      tmem_ld16(tm_lane, r);
+      tmem_ld16(tm_lane + (k & 1) * 16, r);
       tc_fence_before();
 #pragma unroll
-      for (int c = 0; c < 3; ++c) r[13 + c] = mx[c];
+      for (int o = 0; o < 13; ++o) r[o] = prelu_f(fmaf(r[o], p.fu8[o], p.f[16 + o]), p.f[32 + o]);
 #pragma unroll
-      for (int o = 0; o < 16; ++o) r[o] = prelu_f(fmaf(r[o], p.f[o], p.f[16 + o]), p.f[32 + o]);
-      uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)out_pix * 16);
+      for (int c = 0; c < 3; ++c)                      // RGB order: byte 2 - c of the packed maximum
+        r[13 + c] = prelu_f(fmaf((float)((mx_cur >> (8 * (2 - c))) & 0xffu), p.fpool[c], p.fpool[3 + c]), p.f[32 + 13 + c]);
+      uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix_cur * 16);
       o[0] = pack8(r);
       o[1] = pack8(r + 8);
+      mx_cur = mx_next;
+      pix_cur = pix_next;
     }
   }
   tc_fence_before();
@@ -350,28 +380,41 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
   }
 }
 
-// B image of the uint8 form: three bf16 limbs of  w_k * s_c  (27 columns) and of  sum_c w_(c,tap) * t_c
-// (9 columns), rows = output channels.  w: [27][13] ((c*3+ky)*3+kx major).
 }  // namespace BC_NS
 using namespace BC_NS;
 
-bool Umma<act_t>::initial_build_u8(uint8_t** out, const float* w) {
+// B image of the uint8 form: three fp16 limbs of  w_k s_c 2^e(o)  (27 columns) and of
+// 2^e(o) sum_c w_(c,tap) t_c  (9 columns), rows = output channels, K order as the kernel builds A.
+// w: [27][13] ((c*3+ky)*3+kx major, c in RGB order).  unscale[o] = 2^-e(o) (16 floats, 1 for the unused rows).
+bool Umma<act_t>::initial_build_u8(uint8_t** out, const float* w, float* unscale) {
   const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18
   std::vector<uint8_t> img(3 * U8_W, 0);
-  auto put = [&](int o, int col, double v) {
-    for (int limb = 0; limb < 3; ++limb) {
-      __nv_bfloat16 hb = __float2bfloat16_rn((float)v);
-      v -= (double)__bfloat162float(hb);
-      memcpy(img.data() + limb * U8_W + swz<128>((uint32_t)(o * 128 + col * 2)), &hb, 2);
-    }
-  };
+  for (int o = 0; o < 16; ++o) unscale[o] = 1.f;
   for (int o = 0; o < 13; ++o) {
-    for (int c = 0; c < 3; ++c)
-      for (int tap = 0; tap < 9; ++tap) put(o, c * 9 + tap, (double)w[(c * 9 + tap) * 13 + o] / (256.0 * sd[c]));
-    for (int tap = 0; tap < 9; ++tap) {
-      double t = 0.0;
-      for (int c = 0; c < 3; ++c) t += (double)w[(c * 9 + tap) * 13 + o] * (-mean[c] / sd[c]);
-      put(o, 27 + tap, t);
+    double col[U8_K] = {0.0};
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tap = ky * 3 + kx;
+        double t = 0.0;
+        for (int c = 0; c < 3; ++c) {                        // window byte 3*kx + (2 - c): frames are BGR
+          col[u8_k_byte(ky, 3 * kx + 2 - c)] = (double)w[(c * 9 + tap) * 13 + o] / (256.0 * sd[c]);
+          t += (double)w[(c * 9 + tap) * 13 + o] * (-mean[c] / sd[c]);
+        }
+        col[u8_k_valid(ky, kx)] = t;
+      }
+    double mxv = 0.0;
+    for (double v : col) mxv = std::max(mxv, std::fabs(v));
+    int e = 0;
+    if (mxv > 0.0) { int ex; std::frexp(mxv, &ex); e = 14 - ex; }      // largest entry in [2^13, 2^14)
+    e = std::min(std::max(e, -40), 40);
+    unscale[o] = (float)std::ldexp(1.0, -e);
+    for (int k = 0; k < U8_K; ++k) {
+      double v = std::ldexp(col[k], e);
+      for (int limb = 0; limb < 3; ++limb) {
+        const __half hb = __float2half_rn((float)v);
+        v -= (double)__half2float(hb);
+        memcpy(img.data() + limb * U8_W + swz<128>((uint32_t)(o * 128 + k * 2)), &hb, 2);
+      }
     }
   }
   if (cudaMalloc(out, img.size()) != cudaSuccess) return false;
@@ -408,8 +451,8 @@ cudaError_t Umma<act_t>::prepare_initial() {
 }
 
 cudaError_t Umma<act_t>::launch_initial(const void* x, int kind, int B, act_t* out, const uint8_t* wblob, const uint8_t* wblob_u8,
-                                        const float* lut, const float* g, const float* b, const float* a, int num_sms,
-                                        cudaStream_t s) {
+                                        const float* u8_unscale, const float* lut, const float* g, const float* b, const float* a,
+                                        int num_sms, cudaStream_t s) {
   InitParams p{};
   p.num_tiles = B * 256;
   p.x = x;
@@ -419,6 +462,14 @@ cudaError_t Umma<act_t>::launch_initial(const void* x, int kind, int B, act_t* o
   memcpy(p.f, g, 64);
   memcpy(p.f + 16, b, 64);
   memcpy(p.f + 32, a, 64);
+  for (int o = 0; o < 16; ++o) p.fu8[o] = g[o] * u8_unscale[o];
+  {
+    const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18,91
+    for (int c = 0; c < 3; ++c) {
+      p.fpool[c] = (float)((double)g[13 + c] / (256.0 * sd[c]));
+      p.fpool[3 + c] = (float)((double)g[13 + c] * (-mean[c] / sd[c]) + (double)b[13 + c]);
+    }
+  }
   const int smem = INIT_SMEM + 1024;       // opt-in set per device by prepare_initial()
   if (kind == 0 && ((uintptr_t)x & 3) == 0) {          // the byte-window loads are 32-bit: a frame pointer that is not
     const int ctas8 = num_sms * U8_MINB;               // 4-byte aligned takes the byte-wise tf32 kernel below

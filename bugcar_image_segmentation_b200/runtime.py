@@ -38,3 +38,45 @@ def to_device_u8(torch, device, a):
 
 def new_context(device, max_batch=None):
     return _lib.Context(device, DEFAULT_MAX_BATCH if max_batch is None else max_batch)
+
+
+def gpu_numa_node(device):
+    """NUMA node the GPU's PCIe root hangs off (sysfs), or None when the platform does not say."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device)
+        pci = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{pci}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def bind_host_to_gpu(device):
+    """Pin the calling process to the CPUs of the GPU's NUMA node, so that the pinned staging
+    buffers allocated AFTERWARDS (first touch) and the submitting thread are local to the GPU: the
+    H2D stream of a frame batch then never crosses the socket interconnect.  Returns a dict that
+    says what was done ({"node": n, "cpus": k} or {"node": None, ...}); never raises."""
+    node = gpu_numa_node(device)
+    info = {"node": node, "cpus": None, "bound": False}
+    if node is None:
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(cpus=len(cpus), bound=True)
+    except (OSError, ValueError):
+        pass
+    return info
