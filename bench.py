@@ -229,6 +229,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    from bugcar_image_segmentation_b200 import runtime
+    host_bind = runtime.bind_host_to_gpu(local)     # before any pinned allocation: staging buffers local to the GPU's NUMA node
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there
     # when NCCL_DEBUG is set) go to stderr until the result is printed
     sys.stdout.flush()
@@ -284,52 +286,13 @@ def main():
     pinned_out2 = [pinned_out, torch.empty_like(pinned_out).pin_memory()]
 
     def step_e2e(i):
-        if world == 1:
-            # the streaming host entry point: step i's H2D overlaps step i-1's kernels; returns when
-            # step i-1's grids are on the host (one step in flight)
-            model.ctx.pipeline_host_submit(pinned[i % N_INPUT_SETS], 256, 512, B, pipe.lut, *GRID, 0, 0,
-                                           pinned_out2[i & 1], stream.cuda_stream)
-            model.ctx.pipeline_host_wait(1)
-        else:
-            # N > 1: the same overlap with torch streams (the NCCL gather sits between the kernels and
-            # the D2H): H2D of step i on the copy stream while step i-1 computes; one step in flight
-            j = i & 1
-            copy_stream.wait_event(computed[j])                 # step i-2 no longer reads this staging buffer
-            with torch.cuda.stream(copy_stream):
-                stage[j].copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
-                copied[j].record(copy_stream)
-            stream.wait_event(copied[j])
-            if peer is not None:
-                peer.use(i)
-                pipe.run_device(stage[j], to_gather=True)
-                computed[j].record(stream)
-                allg = peer.ready()
-            else:
-                pipe.run_device(stage[j], d_grids)
-                computed[j].record(stream)
-                allg = sharding.gather_grids(d_grids, rank, world)
-            if rank == 0:                                        # the grids leave on their own stream (two gather buffers)
-                gathered[j].record(stream)
-                d2h_stream.wait_event(gathered[j])
-                if peer is None:
-                    allg.record_stream(d2h_stream)                # a fresh tensor per step on the NCCL-gather path
-                with torch.cuda.stream(d2h_stream):
-                    pinned_out2[j].copy_(allg, non_blocking=True)
-                    done[j].record(d2h_stream)
-            else:
-                done[j].record(stream)
-            done[j ^ 1].synchronize()                           # step i-1's grids are on the host
-
-    if world > 1:
-        copy_stream = torch.cuda.Stream()
-        d2h_stream = torch.cuda.Stream()
-        gathered = [torch.cuda.Event() for _ in range(2)]
-        stage = [torch.empty_like(dev_sets[0]) for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        computed = [torch.cuda.Event() for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
-        for e in computed + done:
-            e.record(stream)
+        # the library's streaming host entry point at every N: step i's H2D (internal copy stream) overlaps step
+        # i-1's kernels; returns when step i-1's grids are on the host (one step in flight).  N > 1: the same two
+        # calls per rank -- K9 stores into rank 0's gather buffer, flags in peer-mapped memory order the ranks,
+        # rank 0's context copies each complete step to ITS host buffer (sharding.StreamingGather)
+        model.ctx.pipeline_host_submit(pinned[i % N_INPUT_SETS], 256, 512, B, pipe.lut, *GRID, 0, 0,
+                                       pinned_out2[i & 1] if rank == 0 else None, stream.cuda_stream)
+        model.ctx.pipeline_host_wait(1)
 
     def timed(fn, steps, finish=None):
         barrier()
@@ -360,20 +323,37 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end through the host entry point
-    for i in range(args.warmup):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps, finish=(lambda: model.ctx.pipeline_host_wait(0)) if world == 1 else
-                   (lambda: [e.synchronize() for e in done]))
+    if world == 1:
+        for i in range(args.warmup):
+            step_e2e(i)
+    streaming = None
+    if world > 1:
+        if peer is not None:
+            peer.close()
+        streaming = sharding.StreamingGather(model.ctx, rank, world, B, (Hc, Wc), local)
+        for i in range(args.warmup):
+            step_e2e(i)
+        model.ctx.pipeline_host_wait(0)
+    ms_e2e = timed(step_e2e, args.steps, finish=lambda: model.ctx.pipeline_host_wait(0))
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    # the ceiling the end-to-end number lives under: every rank's bare pinned-host -> device copies of the same
+    # frame batches, all ranks at once, nothing else running (bytes/s summed over the ranks)
+    h2d_stage = torch.empty_like(dev_sets[0])
+    h2d_only = lambda i: h2d_stage.copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
+    for i in range(3):
+        h2d_only(i)
+    ms_h2d = timed(h2d_only, args.steps)
+    h2d_ceiling_gbs = world * B * 393216 * args.steps / (ms_h2d * 1e-3) / 1e9
+    del h2d_stage
+    barrier()
     step_e2e(0)                                          # untimed: grids of input set 0 for the cross-checks
-    if world == 1:
-        model.ctx.pipeline_host_wait(0)
-    else:
-        for e in done:
-            e.synchronize()
+    model.ctx.pipeline_host_wait(0)
     torch.cuda.synchronize()
-    grids_check = pinned_out.numpy()[:B].copy()
+    e2e_out = pinned_out2[0]                             # step_e2e(0) wrote slot 0
+    grids_check = e2e_out.numpy()[:B].copy()
+    if streaming is not None:
+        streaming.close()
 
     # ---- N > 1: what rank 0 holds after the gather == what one GPU computes for the same frames.  Rank 0
     # regenerates 8 sampled frames of EVERY rank's input set 0 (seeds are a function of the rank), pushes them
@@ -381,7 +361,7 @@ def main():
     gather_check = None
     if world > 1:
         if rank == 0:
-            gathered_host = pinned_out.numpy()
+            gathered_host = e2e_out.numpy()
             idx = np.array([0, 31, 32, 63, 128, 200, 254, 255]) % B
             ok = True
             for r in range(world):
@@ -541,7 +521,7 @@ def main():
     # ---- CPU baseline on a bounded sample (rank 0, N = 1)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        threads = os.cpu_count() or 1
+        threads = len(os.sched_getaffinity(0)) or 1       # the cores this process may use (NUMA binding above)
         torch.set_num_threads(threads)
         with open(wpath, "rb") as f:
             w, nc, eps = W.unpack_flat(f.read())
@@ -580,7 +560,13 @@ def main():
                                                                  "peer-mapped buffer (NVLink), one barrier per step"),
                        chunk=args.chunk, tensor_cores=not args.no_tc),
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc},
+                    "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc,
+                    "api": "bc_pipeline_host_submit / bc_pipeline_host_wait on every rank" +
+                           ("" if world == 1 else " + bc_gather_stream_setup (grids peer-stored into rank 0's buffer, flag hand-over, "
+                                                  "D2H by rank 0's context)"),
+                    "h2d_ceiling_gbs": h2d_ceiling_gbs, "h2d_needed_gbs": e2e * 393216 / 1e9,
+                    "e2e_frac_of_h2d_ceiling": e2e * 393216 / 1e9 / h2d_ceiling_gbs,
+                    "host_numa": host_bind},
             "gpu_launches": int(launches), "gather_check": gather_check, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "latency_bs1": latency, "contour_filter": contour, "laserscan": laser, "config5_postprocessing": config5,
             "kernels": kernels,

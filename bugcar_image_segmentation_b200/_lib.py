@@ -50,6 +50,9 @@ SIGNATURES = {
     "bc_pipeline_host_submit": (_i, [_vp, _vp, _i, _i, _i, _vp, _d, _d, _d, _i, _i, _vp, _vp]),
     "bc_pipeline_host_wait": (_i, [_vp, _i]),
     "bc_gather_setup": (_i, [_vp, _vp, _i, _i]),
+    "bc_gather_stream_setup": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "bc_host_alloc": (_i, [C.POINTER(_vp), _sz, _i]),
+    "bc_host_free": (_i, [_vp]),
     "bc_launch_count": (C.c_longlong, [_vp]),
     "bc_set_profile": (_i, [_vp, _i]),
     "bc_profile_json": (C.c_char_p, [_vp]),
@@ -222,6 +225,19 @@ class Context:
     def gather_setup(self, d_base, rank, world):
         self._ck(self.lib.bc_gather_setup(self.h, _ptr(d_base), int(rank), int(world)))
 
+    def gather_stream_setup(self, d_gather, d_arrive, d_release_mine, d_release_peers, rank, world):
+        """d_gather: two device pointers (or None to switch the mode off); d_release_peers: list of `world`
+        device pointers on rank 0, None elsewhere (see include/bugcar_b200.h)"""
+        if d_gather is None:
+            self._ck(self.lib.bc_gather_stream_setup(self.h, None, None, None, None, 0, 1))
+            return
+        ga = (_vp * 2)(*[_ptr(p) for p in d_gather])
+        peers = None
+        if d_release_peers is not None:
+            peers = (_vp * len(d_release_peers))(*[_ptr(p) for p in d_release_peers])
+        self._ck(self.lib.bc_gather_stream_setup(self.h, ga, _ptr(d_arrive), _ptr(d_release_mine), peers,
+                                                 int(rank), int(world)))
+
     def launch_count(self):
         return int(self.lib.bc_launch_count(self.h))
 
@@ -232,6 +248,37 @@ class Context:
         """list of {"kernel", "launches", "ms", "bytes", "flops"} since set_profile(True)"""
         import json
         return json.loads(self.lib.bc_profile_json(self.h).decode())
+
+
+class HostBuffer:
+    """Page-locked host memory from bc_host_alloc as a NumPy array (write_combined: frame staging that the CPU
+    only writes and the GPU only reads)."""
+
+    def __init__(self, shape, dtype, write_combined=False):
+        import numpy as np
+        self.lib = load()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _vp()
+        rc = self.lib.bc_host_alloc(C.byref(p), n, int(bool(write_combined)))
+        if rc != BC_OK:
+            raise BugcarError(rc, "bc_host_alloc failed")
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_uint8 * n).from_address(self.ptr)).view(dtype).reshape(shape)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.lib.bc_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def laser_tables(Wc, Hc, binary):

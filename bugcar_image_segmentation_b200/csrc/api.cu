@@ -158,6 +158,18 @@ struct bc_ctx {
   int8_t* gather_base = nullptr;
   int rank = 0, world = 1;
 
+  // ---- streaming gather (bc_gather_stream_setup): flags in peer-mapped device memory
+  struct GatherStream {
+    bool on = false;
+    int8_t* gather[2] = {nullptr, nullptr};
+    uint32_t* arrive = nullptr;          // rank 0's [2][world]
+    uint32_t* release_mine = nullptr;    // this rank's [2]
+    uint32_t** d_release_peers = nullptr;  // rank 0: device array [2][world] of pointers to every rank's release flag of slot s
+    int* h_err = nullptr;                // pinned, device-mapped: raised by a flag wait that timed out (read without a CUDA call)
+    int* d_err = nullptr;                // its device address
+    long long steps = 0;
+  } gs;
+
   // ---- CUDA graphs of bc_pipeline[_host]
   std::vector<GraphEntry> graphs;
 
@@ -1165,7 +1177,8 @@ void bc_destroy(bc_ctx* c) {
   for (auto e : c->copy_done) if (e) cudaEventDestroy(e);
   if (c->call_start) cudaEventDestroy(c->call_start);
   void* ps[] = {c->d_lut32, c->d_lut64, c->d_labels, c->d_resized, c->d_frames_in, c->d_grids_out, c->cn_scratch,
-                c->d_labels_cn, c->laser_cells, c->laser_first};
+                c->d_labels_cn, c->laser_cells, c->laser_first, c->gs.d_release_peers};
+  if (c->gs.h_err) cudaFreeHost(c->gs.h_err);
   for (auto& t : c->laser_tabs) { cudaFree(t.d_fwd); cudaFree(t.d_inv); }
   for (void* p : ps) if (p) cudaFree(p);
   delete c;
@@ -1547,7 +1560,7 @@ int bc_pipeline_host(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const
 int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B, const uint8_t h_lut[256], double w_m,
                             double h_m, double cell_m, int binary, int ros_layout, int8_t* h_grids, void* stream) {
   if (!c) return BC_ERR_ARG;
-  if (!h_bgr || !h_grids || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
+  if (!h_bgr || !h_lut) return fail(c, BC_ERR_ARG, "null pointer");
   if (h < 1 || w < 1 || h > 16384 || w > 16384) return fail(c, BC_ERR_ARG, "bad frame shape");
   if (B < 1 || B > c->max_batch) return fail(c, BC_ERR_ARG, "batch size outside [1, max_batch]");
   if (!c->net_loaded) return fail(c, BC_ERR_STATE, "bc_load_enet has not been called");
@@ -1558,8 +1571,10 @@ int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B
     return fail(c, BC_ERR_ARG, "calibration input size must be (256, 512) for the ENet pipeline (bev.py:169)");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (c->gs.on && !h_grids && c->rank == 0) return fail(c, BC_ERR_ARG, "rank 0 needs a host buffer for the gathered grids");
+  if (!c->gs.on && !h_grids) return fail(c, BC_ERR_ARG, "null pointer");
   bc_ctx::Slot& sl = c->slots[c->submitted & 1];
-  const size_t in_bytes = (size_t)B * h * w * 3, out_bytes = (size_t)B * g.Hc * g.Wc;
+  const size_t in_bytes = (size_t)B * h * w * 3, out_bytes = c->gs.on ? 0 : (size_t)B * g.Hc * g.Wc;
   if (sl.busy) { CU(cudaEventSynchronize(sl.done)); sl.busy = false; }      // at most two steps in flight
   if (sl.in_bytes < in_bytes || sl.out_bytes < out_bytes) {
     CU(cudaDeviceSynchronize());
@@ -1584,6 +1599,33 @@ int bc_pipeline_host_submit(bc_ctx* c, const uint8_t* h_bgr, int h, int w, int B
   CU(cudaMemcpyAsync(sl.d_in, h_bgr, in_bytes, cudaMemcpyHostToDevice, c->copy_stream));
   CU(cudaEventRecord(sl.copied, c->copy_stream));
   CU(cudaStreamWaitEvent(s, sl.copied, 0));
+  if (c->gs.on) {
+    // multi-GPU streaming gather: this rank's grids go straight into rank 0's buffer of the slot; flags order
+    // the ranks (see bc_gather_stream_setup in the header)
+    bc_ctx::GatherStream& gs = c->gs;
+    const int j = (int)(gs.steps & 1);
+    const uint32_t gen = (uint32_t)(gs.steps / 2 + 1);
+    const size_t cells = (size_t)g.Hc * g.Wc;
+    if (gen > 1) launch_flag_wait(gs.release_mine + j, 1, gen - 1, gs.d_err, s);     // rank 0 has drained the slot's previous step
+    if ((r = run_pipeline(c, sl.d_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, gs.gather[j] + (size_t)c->rank * B * cells, s)))
+      return r;
+    launch_flag_store1(gs.arrive + (size_t)j * c->world + c->rank, gen, s);
+    c->launches += gen > 1 ? 2 : 1;
+    CU(cudaEventRecord(sl.computed, s));
+    if (c->rank == 0) {
+      launch_flag_wait(gs.arrive + (size_t)j * c->world, c->world, gen, gs.d_err, c->d2h_stream);
+      CU(cudaMemcpyAsync(h_grids, gs.gather[j], (size_t)c->world * B * cells, cudaMemcpyDeviceToHost, c->d2h_stream));
+      launch_flag_store(gs.d_release_peers + (size_t)j * c->world, c->world, gen, c->d2h_stream);
+      c->launches += 2;
+      CU(cudaEventRecord(sl.done, c->d2h_stream));
+    } else {
+      CU(cudaEventRecord(sl.done, s));
+    }
+    gs.steps++;
+    sl.busy = true;
+    c->submitted++;
+    return check_launch(c, "streaming gather");
+  }
   if ((r = run_pipeline(c, sl.d_in, h, w, B, h_lut, w_m, h_m, cell_m, g, nullptr, sl.d_out, s))) return r;
   // the grids leave on a third stream, so the next step's kernels (already queued on `s`) start at once
   CU(cudaEventRecord(sl.computed, s));
@@ -1606,6 +1648,10 @@ int bc_pipeline_host_wait(bc_ctx* c, int keep_in_flight) {
     bc_ctx::Slot& sl = c->slots[(c->submitted + k) & 1];
     if (sl.busy) { CU(cudaEventSynchronize(sl.done)); sl.busy = false; }
   }
+  if (c->gs.on) {
+    const int err = *(volatile int*)c->gs.h_err;
+    if (err) return fail(c, BC_ERR_STATE, "streaming gather: a rank did not deliver its grids within the time-out");
+  }
   return BC_OK;
 }
 
@@ -1616,6 +1662,58 @@ int bc_gather_setup(bc_ctx* c, void* d_gather_base, int rank, int world) {
   c->rank = d_gather_base ? rank : 0;
   c->world = d_gather_base ? world : 1;
   return BC_OK;
+}
+
+int bc_gather_stream_setup(bc_ctx* c, void* const d_gather[2], uint32_t* d_arrive, uint32_t* d_release_mine,
+                           uint32_t* const* d_release_peers, int rank, int world) {
+  if (!c) return BC_ERR_ARG;
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  bc_ctx::GatherStream& gs = c->gs;
+  if (gs.d_release_peers) { cudaFree(gs.d_release_peers); gs.d_release_peers = nullptr; }
+  gs.on = false;
+  gs.steps = 0;
+  if (!d_gather) { c->rank = 0; c->world = 1; return BC_OK; }
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(c, BC_ERR_ARG, "rank outside [0, world), world <= 64");
+  if (!d_gather[0] || !d_gather[1] || !d_arrive || !d_release_mine) return fail(c, BC_ERR_ARG, "null pointer");
+  if (rank == 0 && !d_release_peers) return fail(c, BC_ERR_ARG, "rank 0 needs every rank's release flags");
+  gs.gather[0] = (int8_t*)d_gather[0]; gs.gather[1] = (int8_t*)d_gather[1];
+  gs.arrive = d_arrive;
+  gs.release_mine = d_release_mine;
+  if (!gs.h_err) {
+    CU(cudaHostAlloc((void**)&gs.h_err, sizeof(int), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&gs.d_err, gs.h_err, 0));
+  }
+  *gs.h_err = 0;
+  if (rank == 0) {
+    std::vector<uint32_t*> tab((size_t)2 * world);          // [slot][rank] -> &release_r[slot]
+    for (int sidx = 0; sidx < 2; ++sidx)
+      for (int r2 = 0; r2 < world; ++r2) {
+        if (!d_release_peers[r2]) return fail(c, BC_ERR_ARG, "null release-flag pointer");
+        tab[(size_t)sidx * world + r2] = d_release_peers[r2] + sidx;
+      }
+    CU(cudaMalloc(&gs.d_release_peers, tab.size() * sizeof(uint32_t*)));
+    CU(cudaMemcpy(gs.d_release_peers, tab.data(), tab.size() * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+  }
+  c->rank = rank; c->world = world;
+  c->submitted = 0;
+  for (auto& sl : c->slots) sl.busy = false;
+  invalidate_graphs(c);
+  gs.on = true;
+  return BC_OK;
+}
+
+int bc_host_alloc(void** h_ptr, size_t bytes, int write_combined) {
+  if (!h_ptr || bytes == 0) return BC_ERR_ARG;
+  *h_ptr = nullptr;
+  cudaError_t e = cudaHostAlloc(h_ptr, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); g_create_err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return BC_ERR_NOMEM; }
+  return BC_OK;
+}
+
+int bc_host_free(void* h_ptr) {
+  if (!h_ptr) return BC_OK;
+  return cudaFreeHost(h_ptr) == cudaSuccess ? BC_OK : BC_ERR_CUDA;
 }
 
 long long bc_launch_count(const bc_ctx* c) { return c ? c->launches : 0; }

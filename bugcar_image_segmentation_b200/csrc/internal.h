@@ -133,6 +133,11 @@ void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grid
 cudaError_t prepare_occgrid();            // dynamic shared-memory opt-in of K9 on the current device
 
 
+// flag kernels of the streaming gather (prepost.cu): system-scope release store / bounded acquire spin
+void launch_flag_store(uint32_t* const* ptrs, int n, uint32_t value, cudaStream_t s);       // *ptrs[i] = value, i < n (ptrs: device array)
+void launch_flag_store1(uint32_t* ptr, uint32_t value, cudaStream_t s);
+void launch_flag_wait(const uint32_t* flags, int n, uint32_t value, int* d_err, cudaStream_t s);   // until flags[i] >= value for all i < n
+
 // ------------------------------------------------------------------ launchers (contour.cu)
 // contour_noise_removal (image_processing_utils.py:4-44): uint8 masks (B,H,W) -> uint8 0/1 masks.
 // `scratch` must hold contour_scratch_bytes(B,H,W) bytes; needs 50 <= min(H,W) < 1650.

@@ -330,4 +330,40 @@ void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grid
   k_occgrid<<<grid, 128, smem, s>>>(labels, g, B, fpb, grids);
 }
 
+// ------------------------------------------------------------------ streaming gather flags
+// One thread per flag.  The store is a system-scope release: everything this GPU wrote before the kernel
+// (stream order), K9's peer stores included, is visible to whoever acquires the flag.
+__global__ void k_flag_store(uint32_t* const* ptrs, uint32_t* single, int n, uint32_t value) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  uint32_t* p = single ? single : ptrs[i];
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(value) : "memory");
+}
+// Waits until every flag has reached `value` (flags only grow).  Bounded: after ~10 s the kernel gives up and
+// raises *d_err, so a dead peer cannot hang the GPU.
+__global__ void k_flag_wait(const uint32_t* flags, int n, uint32_t value, int* d_err) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  const long long t0 = clock64();
+  uint32_t v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+    if ((int)(v - value) >= 0) break;
+    __nanosleep(200);
+    if (clock64() - t0 > 20000000000LL) {            // ~10 s at 1.9 GHz
+      *(volatile int*)d_err = 1;
+      __threadfence_system();
+      break;
+    }
+  }
+}
+void launch_flag_store(uint32_t* const* ptrs, int n, uint32_t value, cudaStream_t s) {
+  k_flag_store<<<1, 32, 0, s>>>(ptrs, nullptr, n, value);
+}
+void launch_flag_store1(uint32_t* ptr, uint32_t value, cudaStream_t s) { k_flag_store<<<1, 32, 0, s>>>(nullptr, ptr, 1, value); }
+void launch_flag_wait(const uint32_t* flags, int n, uint32_t value, int* d_err, cudaStream_t s) {
+  k_flag_wait<<<1, 32, 0, s>>>(flags, n, value, d_err);
+}
+
 }  // namespace bc

@@ -81,3 +81,58 @@ class PeerGather:
 
     def close(self):
         self.ctx.gather_setup(None, 0, 1)
+
+
+def _share(t):
+    return t.untyped_storage()._share_cuda_()
+
+
+def _open(handle, device, shape, dtype):
+    h = list(handle)
+    h[0] = device                                   # open the mapping on THIS rank's device
+    storage = torch.UntypedStorage._new_shared_cuda(*h)
+    return torch.empty(0, dtype=dtype, device=f"cuda:{device}").set_(storage, 0, shape)
+
+
+class StreamingGather:
+    """The multi-GPU form of ``bc_pipeline_host_submit`` / ``_wait`` (``bc_gather_stream_setup``): every rank
+    submits ITS frame batches from pinned host memory; the occupancy-grid kernels store into rank 0's gather
+    buffer over NVLink, the ranks hand over through flags in peer-mapped device memory, and rank 0's library
+    context copies each complete (world*B, Hc, Wc) step to rank 0's host buffer.  torch.distributed is used
+    once, here, to exchange the CUDA IPC handles; no collective runs per step.
+
+        sg = StreamingGather(ctx, rank, world, B, (Hc, Wc), device)
+        ctx.pipeline_host_submit(pinned_frames, h, w, B, lut, ..., host_grids if rank == 0 else None, stream)
+        ctx.pipeline_host_wait(1)
+    """
+
+    def __init__(self, ctx, rank, world, B, grid_shape, device):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        dev = f"cuda:{device}"
+        shape = (world * B,) + tuple(grid_shape)
+        handles = [None]
+        if rank == 0:
+            self.gather = [torch.zeros(shape, dtype=torch.int8, device=dev) for _ in range(2)]
+            self.arrive = torch.zeros((2, world), dtype=torch.int32, device=dev)
+            handles = [[_share(self.gather[0]), _share(self.gather[1]), _share(self.arrive)]]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            g0, g1, ar = handles[0]
+            self.gather = [_open(g0, device, shape, torch.int8), _open(g1, device, shape, torch.int8)]
+            self.arrive = _open(ar, device, (2, world), torch.int32)
+        self.release = torch.zeros(2, dtype=torch.int32, device=dev)          # this rank's own flags
+        torch.cuda.synchronize()
+        rel = [None] * world
+        dist.all_gather_object(rel, _share(self.release) if rank != 0 else None)
+        peers = None
+        if rank == 0:
+            self.release_peers = [self.release] + [_open(rel[r], device, (2,), torch.int32) for r in range(1, world)]
+            peers = [t.data_ptr() for t in self.release_peers]
+        dist.barrier()
+        ctx.gather_stream_setup([g.data_ptr() for g in self.gather], self.arrive.data_ptr(), self.release.data_ptr(),
+                                peers, rank, world)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.ctx.gather_stream_setup(None, None, None, None, 0, 1)

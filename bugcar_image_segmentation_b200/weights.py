@@ -20,7 +20,18 @@ Flat container ("BCENETW1"), little endian:
     which begins at the first 64-byte boundary after the table)
 A missing ``*.weight`` for an activation means ReLU (decoder_relu=True in the
 canonical model); a 1-element activation weight is a shared PReLU slope, a
-C-element one is per-channel.
+C-element one is per-channel.  A ``<conv>.bias`` tensor next to a ``<conv>.weight`` is a
+convolution bias (folded into the batch-norm shift at load time).
+
+The network GRAPH travels in the container too (real blobs of this family differ in details,
+SURVEY.md section 7 hard part 1), as two reserved tensors:
+    ``__graph__``  float32 [n_blocks][7]: kind (0 down, 1 regular/dilated, 2 asymmetric, 3 up), stage,
+                   index, cin, cout, internal width, dilation -- the block's parameter prefix is
+                   ``{downsample|regular|dilated|asymmetric|upsample}{stage}_{index}``
+    ``__spec__``   float32 [4]: initial max-pool kernel (3: 3x3 s2 p1 as PyTorch-ENet, 2: 2x2 s2 as the
+                   paper / Keras ports), head kernel (3: ConvTranspose 3x3 s2 p1 op1, 2: 2x2 s2), 0, 0
+Absent tensors mean the canonical graph (ENET_BLOCKS) and (3, 3).  The C loader validates the list
+against what its kernels implement and every parameter shape against the list.
 """
 import struct
 
@@ -53,72 +64,109 @@ ENET_BLOCKS = [
 DECODER_BLOCKS = {"upsample4_0", "regular4_1", "regular4_2", "upsample5_0", "regular5_1"}
 
 
+KIND_CODE = {"down": 0, "reg": 1, "asym": 2, "up": 3}
+
+
+def graph_rows(blocks=None, down_internal="in/4"):
+    """ENET_BLOCKS-style list -> float32 [n][7] rows of the container's ``__graph__`` tensor"""
+    rows = []
+    for name, kind, args in (ENET_BLOCKS if blocks is None else blocks):
+        import re
+        m = re.match(r"[a-z]+(\d+)_(\d+)$", name)
+        stage, index = int(m.group(1)), int(m.group(2))
+        if kind in ("down", "up"):
+            cin, cout = args
+            ci = (cout if down_internal == "out/4" and kind == "down" else cin) // 4
+            dil = 1
+        else:
+            cin = cout = args[0]
+            ci = cin // 4
+            dil = args[1] if kind == "reg" else 1
+        rows.append([KIND_CODE[kind], stage, index, cin, cout, ci, dil])
+    return np.asarray(rows, np.float32)
+
+
+def block_name(kind_code, stage, index, dilation):
+    base = {0: "downsample", 1: "regular" if dilation == 1 else "dilated", 2: "asymmetric", 3: "upsample"}[int(kind_code)]
+    return f"{base}{int(stage)}_{int(index)}"
+
+
 def _bn(prefix, c):
     return [(prefix + ".weight", (c,), "bn_gamma"), (prefix + ".bias", (c,), "bn_beta"),
             (prefix + ".running_mean", (c,), "bn_mean"), (prefix + ".running_var", (c,), "bn_var")]
 
 
-def enet_param_spec(num_classes=15, encoder_relu=False, decoder_relu=True):
+def enet_param_spec(num_classes=15, encoder_relu=False, decoder_relu=True, prelu_per_channel=False, conv_bias=False,
+                    head_kernel=3, blocks=None):
     """Ordered list of (name, shape, kind) for every parameter of the network."""
     spec = []
+    last_ch = [16]
 
-    def act(name, relu):
+    def act(name, relu, ch=None):
         if not relu:
-            spec.append((name + ".weight", (1,), "prelu"))
+            spec.append((name + ".weight", ((ch if ch else last_ch[0]) if prelu_per_channel else 1,), "prelu"))
 
-    spec.append(("initial_block.main_branch.weight", (13, 3, 3, 3), "conv"))
+    def conv(name, shape, kind="conv"):
+        spec.append((name + ".weight", shape, kind))
+        cout = shape[1] if kind == "tconv" else shape[0]
+        if conv_bias and name != "transposed_conv":
+            spec.append((name + ".bias", (cout,), "bias"))
+        last_ch[0] = cout
+
+    conv("initial_block.main_branch", (13, 3, 3, 3))
     spec.extend(_bn("initial_block.batch_norm", 16))
-    act("initial_block.out_activation", encoder_relu)
-    for name, kind, args in ENET_BLOCKS:
+    act("initial_block.out_activation", encoder_relu, 16)
+    for name, kind, args in (ENET_BLOCKS if blocks is None else blocks):
         relu = decoder_relu if name in DECODER_BLOCKS else encoder_relu
         if kind == "down":
             cin, cout = args
             ci = cin // 4
-            spec.append((f"{name}.ext_conv1.0.weight", (ci, cin, 2, 2), "conv"))
+            conv(f"{name}.ext_conv1.0", (ci, cin, 2, 2))
             spec.extend(_bn(f"{name}.ext_conv1.1", ci)); act(f"{name}.ext_conv1.2", relu)
-            spec.append((f"{name}.ext_conv2.0.weight", (ci, ci, 3, 3), "conv"))
+            conv(f"{name}.ext_conv2.0", (ci, ci, 3, 3))
             spec.extend(_bn(f"{name}.ext_conv2.1", ci)); act(f"{name}.ext_conv2.2", relu)
-            spec.append((f"{name}.ext_conv3.0.weight", (cout, ci, 1, 1), "conv"))
+            conv(f"{name}.ext_conv3.0", (cout, ci, 1, 1))
             spec.extend(_bn(f"{name}.ext_conv3.1", cout)); act(f"{name}.ext_conv3.2", relu)
-            act(f"{name}.out_activation", relu)
+            act(f"{name}.out_activation", relu, cout)
         elif kind in ("reg", "asym"):
             ch = args[0]
             ci = ch // 4
-            spec.append((f"{name}.ext_conv1.0.weight", (ci, ch, 1, 1), "conv"))
+            conv(f"{name}.ext_conv1.0", (ci, ch, 1, 1))
             spec.extend(_bn(f"{name}.ext_conv1.1", ci)); act(f"{name}.ext_conv1.2", relu)
             if kind == "reg":
-                spec.append((f"{name}.ext_conv2.0.weight", (ci, ci, 3, 3), "conv"))
+                conv(f"{name}.ext_conv2.0", (ci, ci, 3, 3))
                 spec.extend(_bn(f"{name}.ext_conv2.1", ci)); act(f"{name}.ext_conv2.2", relu)
             else:
-                spec.append((f"{name}.ext_conv2.0.weight", (ci, ci, 5, 1), "conv"))
+                conv(f"{name}.ext_conv2.0", (ci, ci, 5, 1))
                 spec.extend(_bn(f"{name}.ext_conv2.1", ci)); act(f"{name}.ext_conv2.2", relu)
-                spec.append((f"{name}.ext_conv2.3.weight", (ci, ci, 1, 5), "conv"))
+                conv(f"{name}.ext_conv2.3", (ci, ci, 1, 5))
                 spec.extend(_bn(f"{name}.ext_conv2.4", ci)); act(f"{name}.ext_conv2.5", relu)
-            spec.append((f"{name}.ext_conv3.0.weight", (ch, ci, 1, 1), "conv"))
+            conv(f"{name}.ext_conv3.0", (ch, ci, 1, 1))
             spec.extend(_bn(f"{name}.ext_conv3.1", ch)); act(f"{name}.ext_conv3.2", relu)
-            act(f"{name}.out_activation", relu)
+            act(f"{name}.out_activation", relu, ch)
         elif kind == "up":
             cin, cout = args
             ci = cin // 4
-            spec.append((f"{name}.main_conv1.0.weight", (cout, cin, 1, 1), "conv"))
+            conv(f"{name}.main_conv1.0", (cout, cin, 1, 1))
             spec.extend(_bn(f"{name}.main_conv1.1", cout))
-            spec.append((f"{name}.ext_conv1.0.weight", (ci, cin, 1, 1), "conv"))
+            conv(f"{name}.ext_conv1.0", (ci, cin, 1, 1))
             spec.extend(_bn(f"{name}.ext_conv1.1", ci)); act(f"{name}.ext_conv1.2", relu)
-            spec.append((f"{name}.ext_tconv1.weight", (ci, ci, 2, 2), "tconv"))
+            conv(f"{name}.ext_tconv1", (ci, ci, 2, 2), "tconv")
             spec.extend(_bn(f"{name}.ext_tconv1_bnorm", ci)); act(f"{name}.ext_tconv1_activation", relu)
-            spec.append((f"{name}.ext_conv2.0.weight", (cout, ci, 1, 1), "conv"))
+            conv(f"{name}.ext_conv2.0", (cout, ci, 1, 1))
             spec.extend(_bn(f"{name}.ext_conv2.1", cout))
-            act(f"{name}.out_activation", relu)
-    spec.append(("transposed_conv.weight", (16, num_classes, 3, 3), "tconv"))
+            act(f"{name}.out_activation", relu, cout)
+    spec.append(("transposed_conv.weight", (16, num_classes, head_kernel, head_kernel), "tconv"))
     return spec
 
 
-def synthetic_weights(seed=42, num_classes=15, encoder_relu=False, decoder_relu=True):
+def synthetic_weights(seed=42, num_classes=15, encoder_relu=False, decoder_relu=True, **variant):
     """Seeded generator: He-scaled conv weights,
-    BN gamma~U(0.5,1.5), beta~N(0,0.1), mean~N(0,0.1), var~U(0.5,1.5), PReLU 0.25."""
+    BN gamma~U(0.5,1.5), beta~N(0,0.1), mean~N(0,0.1), var~U(0.5,1.5), PReLU 0.25
+    (per-channel variant: U(0.05, 0.45)), conv biases N(0, 0.1).  ``variant``: see enet_param_spec."""
     rng = np.random.default_rng(seed)
     out = {}
-    for name, shape, kind in enet_param_spec(num_classes, encoder_relu, decoder_relu):
+    for name, shape, kind in enet_param_spec(num_classes, encoder_relu, decoder_relu, **variant):
         if kind == "conv":
             fan_in = shape[1] * shape[2] * shape[3]
             w = rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)
@@ -132,15 +180,23 @@ def synthetic_weights(seed=42, num_classes=15, encoder_relu=False, decoder_relu=
         elif kind == "bn_var":
             w = rng.uniform(0.5, 1.5, shape)
         elif kind == "prelu":
-            w = np.full(shape, 0.25)
+            w = np.full(shape, 0.25) if shape == (1,) else rng.uniform(0.05, 0.45, shape)
+        elif kind == "bias":
+            w = rng.standard_normal(shape) * 0.1
         else:
             raise ValueError(kind)
         out[name] = np.ascontiguousarray(w, dtype=np.float32)
     return out
 
 
-def pack_flat(weights, num_classes=None, bn_eps=BN_EPS):
-    """dict name -> float32 ndarray (<= 4 dims)  ->  bytes of the flat container."""
+def pack_flat(weights, num_classes=None, bn_eps=BN_EPS, graph=None, initial_pool=None, head_kernel=None):
+    """dict name -> float32 ndarray (<= 4 dims)  ->  bytes of the flat container.  ``graph`` (graph_rows),
+    ``initial_pool`` and ``head_kernel`` add the reserved ``__graph__`` / ``__spec__`` tensors."""
+    weights = dict(weights)
+    if graph is not None:
+        weights["__graph__"] = np.asarray(graph, np.float32)
+    if initial_pool is not None or head_kernel is not None:
+        weights["__spec__"] = np.asarray([initial_pool or 3, head_kernel or 3, 0, 0], np.float32)
     names = list(weights.keys())
     if num_classes is None:
         num_classes = int(weights["transposed_conv.weight"].shape[1])

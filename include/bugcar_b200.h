@@ -201,6 +201,32 @@ int bc_pipeline_host_wait(bc_ctx* ctx, int keep_in_flight);
  * so K9's stores travel over NVLink; pass NULL to switch the redirection off. */
 int bc_gather_setup(bc_ctx* ctx, void* d_gather_base, int rank, int world);
 
+/* Streaming gather: makes bc_pipeline_host_submit / _wait the multi-GPU entry point.  One process per
+ * GPU calls submit with ITS frames; the occupancy-grid kernel of every rank stores into rank 0's
+ * gather buffer (as with bc_gather_setup), and the ranks synchronise through flags in peer-mapped
+ * device memory -- no collective, no host barrier per step:
+ *   - after its kernels rank r writes the step number into d_arrive[slot][r] (rank 0's memory);
+ *   - rank 0 waits (on its internal D2H stream) for all `world` arrivals of the slot, copies the whole
+ *     (world*B, Hc, Wc) buffer to ITS h_grids, then writes the step number into every rank's
+ *     d_release[slot] (that rank's own memory), which that rank's next use of the slot waits for.
+ * Two slots alternate, so step i+1 computes while step i's grids leave.  All pointers are device
+ * pointers valid in this process (CUDA IPC mappings where the memory lives on another GPU):
+ *   d_gather[2]       rank 0's two gather buffers, each world * B * Hc * Wc bytes
+ *   d_arrive          rank 0's memory, uint32 [2][world], zero-initialised
+ *   d_release_mine    this rank's own memory, uint32 [2], zero-initialised
+ *   d_release_peers   rank 0 only: [world] pointers, entry r = rank r's d_release_mine; NULL elsewhere
+ * h_grids of submit is used on rank 0 only (size world * B * Hc * Wc) and may be NULL elsewhere.  A rank
+ * that waits longer than ~10 s for a flag gives up; bc_pipeline_host_wait then returns BC_ERR_STATE.
+ * Pass d_gather == NULL to switch the mode off. */
+int bc_gather_stream_setup(bc_ctx* ctx, void* const d_gather[2], uint32_t* d_arrive, uint32_t* d_release_mine,
+                           uint32_t* const* d_release_peers, int rank, int world);
+
+/* Page-locked host memory for the frame / grid buffers of the *_host calls (cudaHostAlloc).
+ * write_combined = 1 gives write-combined pages: fast for the CPU to fill and for the GPU to
+ * read over PCIe, slow for the CPU to read back -- for frame staging buffers only. */
+int bc_host_alloc(void** h_ptr, size_t bytes, int write_combined);
+int bc_host_free(void* h_ptr);
+
 /* number of kernels this context launched since creation (bench.py "gpu_launches") */
 long long bc_launch_count(const bc_ctx* ctx);
 /* Per-kernel timing for the roofline report: while enabled every launch is bracketed by a

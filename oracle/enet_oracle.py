@@ -18,7 +18,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from bugcar_image_segmentation_b200.weights import ENET_BLOCKS, BN_EPS
+from bugcar_image_segmentation_b200.weights import ENET_BLOCKS, BN_EPS, block_name
 
 
 def _t(a):
@@ -28,6 +28,16 @@ def _t(a):
 class _Net:
     def __init__(self, weights, bn_eps=BN_EPS, emulate=None, calibrate=False):
         self.w = {k: _t(v) for k, v in weights.items()}
+        # graph and variant switches travel with the weights (weights.py: __graph__ / __spec__)
+        spec = weights.get("__spec__")
+        self.initial_pool = int(spec[0]) if spec is not None else 3
+        self.head_kernel = int(spec[1]) if spec is not None else 3
+        g = weights.get("__graph__")
+        if g is None:
+            self.blocks = [(n, k, (a[1] if k == "reg" else 1)) for n, k, a in ENET_BLOCKS]
+        else:
+            kinds = {0: "down", 1: "reg", 2: "asym", 3: "up"}
+            self.blocks = [(block_name(r[0], r[1], r[2], r[6]), kinds[int(r[0])], int(r[6])) for r in np.asarray(g)]
         self.eps = bn_eps
         self.emulate = emulate            # None | "bf16" | "fp16": the 16-bit storage type to emulate
         self.qdtype = {None: None, "bf16": torch.bfloat16, "fp16": torch.float16}[emulate]
@@ -58,21 +68,25 @@ class _Net:
         """conv (no bias) followed by eval-mode BN.  In bf16 emulation the BN is
         folded into bf16 weights + fp32 bias, as the CUDA loader does."""
         W = self.w[conv + ".weight"]
+        cb = self.w.get(conv + ".bias")                  # optional convolution bias (checkpoints built with bias=True)
         if self.emulate:
             g = self.w[bn + ".weight"] / torch.sqrt(self.w[bn + ".running_var"] + self.eps)
             b = self.w[bn + ".bias"] - self.w[bn + ".running_mean"] * g
+            if cb is not None:
+                b = b + cb * g
             if transposed:
                 Wf = (W * g.view(1, -1, 1, 1)).to(self.qdtype).to(torch.float32)
                 return F.conv_transpose2d(x, Wf, b, **kw)
             Wf = (W * g.view(-1, 1, 1, 1)).to(self.qdtype).to(torch.float32)
             return F.conv2d(x, Wf, b, **kw)
-        y = F.conv_transpose2d(x, W, None, **kw) if transposed else F.conv2d(x, W, None, **kw)
+        y = F.conv_transpose2d(x, W, cb, **kw) if transposed else F.conv2d(x, W, cb, **kw)
         return self.bn(y, bn)
 
     # ---- blocks
     def initial(self, x):
-        main = F.conv2d(x, self.w["initial_block.main_branch.weight"], None, stride=2, padding=1)
-        ext = F.max_pool2d(x, 3, stride=2, padding=1)
+        main = F.conv2d(x, self.w["initial_block.main_branch.weight"], self.w.get("initial_block.main_branch.bias"),
+                        stride=2, padding=1)
+        ext = F.max_pool2d(x, 3, stride=2, padding=1) if self.initial_pool == 3 else F.max_pool2d(x, 2, stride=2)
         out = self.bn(torch.cat((main, ext), 1), "initial_block.batch_norm")
         return self.q(self.act(out, "initial_block.out_activation"))
 
@@ -109,24 +123,27 @@ class _Net:
         inter = {}
         x = self.initial(x)
         inter["initial_block"] = x
-        pool_idx = {}
-        sizes = {}
-        for name, kind, args in ENET_BLOCKS:
+        pools = []                                       # (indices, pre-pool size) of the down-sampling blocks, innermost last
+        for name, kind, dil in self.blocks:
             if kind == "down":
-                sizes[name] = x.shape[2:]
-                x, pool_idx[name] = self.down(x, name)
+                size = x.shape[2:]
+                x, idx = self.down(x, name)
+                pools.append((idx, size))
             elif kind == "reg":
-                x = self.regular(x, name, dilation=args[1])
+                x = self.regular(x, name, dilation=dil)
             elif kind == "asym":
                 x = self.regular(x, name, asym=True)
-            elif kind == "up":
-                src = "downsample2_0" if name == "upsample4_0" else "downsample1_0"
-                x = self.up(x, name, pool_idx[src], sizes[src])
+            elif kind == "up":                           # pairs with the innermost open down-sampling block
+                idx, size = pools.pop()
+                x = self.up(x, name, idx, size)
             inter[name] = x
         W = self.w["transposed_conv.weight"]
         if self.emulate:
             W = W.to(self.qdtype).to(torch.float32)
-        logits = F.conv_transpose2d(x, W, None, stride=2, padding=1, output_padding=1)
+        if self.head_kernel == 3:
+            logits = F.conv_transpose2d(x, W, None, stride=2, padding=1, output_padding=1)
+        else:
+            logits = F.conv_transpose2d(x, W, None, stride=2)
         if return_intermediates:
             return logits, inter
         return logits
