@@ -86,6 +86,7 @@ struct bc_ctx {
   long long launches = 0;
 
   int precision = BC_PREC_FP16;
+  int initial_pool = 3;     // max-pool of the initial block: 3 = 3x3 s2 p1, 2 = 2x2 s2 (container "__spec__")
   int chunk = 0;            // 0 = default
   int tensor_cores = 1;
   bool umma_ready = false;
@@ -357,6 +358,12 @@ int fold_conv(bc_ctx* c, const Container& ct, const std::string& conv, const std
   out.cin = cin; out.cout = cout; out.ntaps = kh * kw;
   out.w.resize((size_t)kh * kw * cin * cout);
   out.bias.resize(cout);
+  // an optional convolution bias (checkpoints built with bias=True) goes through the batch norm with the output:
+  // BN(conv + cb) = conv * g + (b + cb * g)
+  if (const Tensor* cb = find(ct, conv + ".bias")) {
+    if (cb->count() != (size_t)cout) return fail(c, BC_ERR_FORMAT, conv + ".bias: expected one value per output channel");
+    for (int o = 0; o < cout; ++o) b[o] += (double)cb->data[o] * g[o];
+  }
   for (int o = 0; o < cout; ++o) out.bias[o] = (float)b[o];
   for (int ky = 0; ky < kh; ++ky)
     for (int kx = 0; kx < kw; ++kx)
@@ -372,7 +379,8 @@ int fold_conv(bc_ctx* c, const Container& ct, const std::string& conv, const std
 }
 
 struct BlockSpec { const char* name; int kind; int a, b; };
-// canonical ENet encoder/decoder (weights.py ENET_BLOCKS)
+// canonical ENet encoder/decoder (weights.py ENET_BLOCKS): used when the container carries no
+// "__graph__" tensor
 const BlockSpec kBlocks[] = {
     {"downsample1_0", 0, 16, 64},
     {"regular1_1", 1, 64, 1}, {"regular1_2", 1, 64, 1}, {"regular1_3", 1, 64, 1}, {"regular1_4", 1, 64, 1},
@@ -387,11 +395,94 @@ const BlockSpec kBlocks[] = {
     {"regular5_1", 1, 16, 1},
 };
 
+// One block of the graph as the container describes it (weights.py "__graph__": kind, stage, index, cin, cout,
+// internal width, dilation) or as kBlocks implies it.
+struct GraphRow { std::string name; int kind, cin, cout, ci, dilation; };
+
+// The block list of this network, checked against what the kernels implement: the channel chain 16 -> ... -> 16,
+// every down-sampling block closed by an up-sampling one of the mirrored widths, and per block the widths the
+// CUDA-core kernels are instantiated for (every tcgen05 kernel covers a subset of those and falls back to them).
+int read_graph(bc_ctx* c, const Container& ct, std::vector<GraphRow>& rows) {
+  rows.clear();
+  const Tensor* g = find(ct, "__graph__");
+  if (!g) {
+    for (const BlockSpec& s : kBlocks) {
+      GraphRow r;
+      r.name = s.name; r.kind = s.kind;
+      if (s.kind == 0 || s.kind == 3) { r.cin = s.a; r.cout = s.b; r.dilation = 1; }
+      else { r.cin = r.cout = s.a; r.dilation = s.b; }
+      r.ci = r.cin / 4;
+      rows.push_back(r);
+    }
+    return BC_OK;
+  }
+  if (g->ndim != 2 || g->dims[1] != 7 || g->dims[0] < 1 || g->dims[0] > 256)
+    return fail(c, BC_ERR_FORMAT, "__graph__: expected [n_blocks][7] with 1 <= n_blocks <= 256");
+  static const char* base[4] = {"downsample", "regular", "asymmetric", "upsample"};
+  for (int i = 0; i < g->dims[0]; ++i) {
+    const float* v = g->data + (size_t)i * 7;
+    for (int k = 0; k < 7; ++k)
+      if (!(v[k] >= 0.f && v[k] <= 4096.f) || v[k] != std::floor(v[k])) return fail(c, BC_ERR_FORMAT, "__graph__: entries must be small non-negative integers");
+    GraphRow r;
+    r.kind = (int)v[0]; r.cin = (int)v[3]; r.cout = (int)v[4]; r.ci = (int)v[5]; r.dilation = (int)v[6];
+    if (r.kind > 3) return fail(c, BC_ERR_FORMAT, "__graph__: unknown block kind");
+    char nm[64];
+    snprintf(nm, sizeof nm, "%s%d_%d", (r.kind == 1 && r.dilation != 1) ? "dilated" : base[r.kind], (int)v[1], (int)v[2]);
+    r.name = nm;
+    rows.push_back(r);
+  }
+  // structural validation
+  int ch = 16, level = 0;
+  std::vector<int> open_down;          // input width of the open down-sampling blocks
+  for (const GraphRow& r : rows) {
+    char msg[256];
+    auto bad = [&](const char* why) {
+      snprintf(msg, sizeof msg, "%s (cin %d, cout %d, internal %d, dilation %d): %s", r.name.c_str(), r.cin, r.cout, r.ci, r.dilation, why);
+      return fail(c, BC_ERR_FORMAT, msg);
+    };
+    if (r.cin != ch) return bad("input width does not match the previous block's output");
+    if (r.kind == 0) {
+      if (!((r.cin == 16 && r.cout == 64) || (r.cin == 64 && r.cout == 128))) return bad("down-sampling blocks are implemented for 16->64 and 64->128");
+      if (r.ci != r.cin / 4) return bad("down-sampling blocks are implemented with internal width cin/4 (the out/4 variant of the paper is not)");
+      if (level >= 2) return bad("more than two down-sampling levels");
+      open_down.push_back(r.cin); ++level;
+    } else if (r.kind == 3) {
+      if (open_down.empty()) return bad("up-sampling block without an open down-sampling block");
+      if (!((r.cin == 128 && r.cout == 64) || (r.cin == 64 && r.cout == 16)) || r.ci != r.cin / 4) return bad("up-sampling blocks are implemented for 128->64 and 64->16 with internal width cin/4");
+      if (r.cout != open_down.back()) return bad("output width must equal the input width of the down-sampling block it mirrors");
+      open_down.pop_back(); --level;
+    } else {
+      if (r.cin != r.cout) return bad("regular / asymmetric blocks keep their width");
+      if (r.ci != r.cin / 4) return bad("internal width must be a quarter of the block width");
+      if (!(r.cin == 64 || r.cin == 128 || (r.cin == 16 && r.kind == 1 && r.dilation == 1))) return bad("implemented widths: 64, 128, and 16 (plain 3x3 only)");
+      if (r.kind == 1 && (r.dilation < 1 || r.dilation > 16)) return bad("dilation must be in [1, 16]");
+      if (r.kind == 2 && r.cin != 128) return bad("asymmetric blocks are implemented at width 128");
+      if ((r.cin == 64 && level != 1) || (r.cin == 128 && level != 2) || (r.cin == 16 && level != 0)) return bad("width does not match the resolution level");
+    }
+    ch = r.cout;
+  }
+  if (!open_down.empty() || ch != 16) return fail(c, BC_ERR_FORMAT, "__graph__: the decoder must return to 16 channels at full block resolution");
+  return BC_OK;
+}
+
 int build_host_net(bc_ctx* c, const Container& ct) {
   int r;
   c->num_classes = ct.num_classes;
   c->bn_eps = ct.bn_eps;
   if (ct.num_classes < 1 || ct.num_classes > 32) return fail(c, BC_ERR_FORMAT, "num_classes must be in [1, 32]");
+  // variant switches (weights.py "__spec__"): initial max-pool kernel, head kernel
+  c->initial_pool = 3;
+  int head_kernel = 3;
+  if (const Tensor* sp = find(ct, "__spec__")) {
+    if (sp->count() < 2) return fail(c, BC_ERR_FORMAT, "__spec__: expected at least 2 entries");
+    c->initial_pool = (int)sp->data[0];
+    head_kernel = (int)sp->data[1];
+    if (c->initial_pool != 2 && c->initial_pool != 3) return fail(c, BC_ERR_FORMAT, "__spec__: initial max-pool kernel must be 2 (2x2 s2) or 3 (3x3 s2 p1)");
+    if (head_kernel != 2 && head_kernel != 3) return fail(c, BC_ERR_FORMAT, "__spec__: head kernel must be 2 (2x2 s2) or 3 (3x3 s2 p1 op1)");
+  }
+  if (find(ct, "transposed_conv.bias")) return fail(c, BC_ERR_FORMAT, "transposed_conv.bias: a bias on the class head is not implemented");
+  std::vector<GraphRow> graph;
+  if ((r = read_graph(c, ct, graph))) return r;
   // initial block: raw conv weights, BN as a per-channel affine on all 16 channels
   {
     const Tensor* w;
@@ -405,23 +496,27 @@ int build_host_net(bc_ctx* c, const Container& ct) {
             c->h_init_w[((ch * 3 + ky) * 3 + kx) * 13 + o] = w->data[((o * 3 + ch) * 3 + ky) * 3 + kx];
     std::vector<double> g, b;
     if ((r = bn_fold(c, ct, "initial_block.batch_norm", 16, g, b))) return r;
+    if (const Tensor* cb = find(ct, "initial_block.main_branch.bias")) {
+      if (cb->count() != 13) return fail(c, BC_ERR_FORMAT, "initial_block.main_branch.bias: expected 13 values");
+      for (int i = 0; i < 13; ++i) b[i] += (double)cb->data[i] * g[i];
+    }
     c->h_init_g.resize(16); c->h_init_b.resize(16);
     for (int i = 0; i < 16; ++i) { c->h_init_g[i] = (float)g[i]; c->h_init_b[i] = (float)b[i]; }
     if ((r = act_alpha(c, ct, "initial_block.out_activation", 16, c->h_init_a))) return r;
   }
   c->h_blocks.clear();
-  for (const BlockSpec& s : kBlocks) {
+  for (const GraphRow& s : graph) {
     HostBlock hb;
     hb.name = s.name;
     hb.kind = s.kind;
     std::string n = s.name;
     if (s.kind == 0) {          // downsample: cin -> cout, internal cin/4
-      hb.cin = s.a; hb.cout = s.b; hb.ci = s.a / 4;
+      hb.cin = s.cin; hb.cout = s.cout; hb.ci = s.ci;
       if ((r = fold_conv(c, ct, n + ".ext_conv1.0", n + ".ext_conv1.1", n + ".ext_conv1.2", true, hb.cin, hb.ci, 2, 2, false, hb.c1))) return r;
       if ((r = fold_conv(c, ct, n + ".ext_conv2.0", n + ".ext_conv2.1", n + ".ext_conv2.2", true, hb.ci, hb.ci, 3, 3, false, hb.c2))) return r;
       if ((r = fold_conv(c, ct, n + ".ext_conv3.0", n + ".ext_conv3.1", n + ".ext_conv3.2", true, hb.ci, hb.cout, 1, 1, false, hb.c3))) return r;
     } else if (s.kind == 1 || s.kind == 2) {
-      hb.cin = hb.cout = s.a; hb.ci = s.a / 4; hb.dilation = s.b;
+      hb.cin = hb.cout = s.cin; hb.ci = s.ci; hb.dilation = s.dilation;
       if ((r = fold_conv(c, ct, n + ".ext_conv1.0", n + ".ext_conv1.1", n + ".ext_conv1.2", true, hb.cin, hb.ci, 1, 1, false, hb.c1))) return r;
       if (s.kind == 1) {
         if ((r = fold_conv(c, ct, n + ".ext_conv2.0", n + ".ext_conv2.1", n + ".ext_conv2.2", true, hb.ci, hb.ci, 3, 3, false, hb.c2))) return r;
@@ -431,7 +526,7 @@ int build_host_net(bc_ctx* c, const Container& ct) {
       }
       if ((r = fold_conv(c, ct, n + ".ext_conv3.0", n + ".ext_conv3.1", n + ".ext_conv3.2", true, hb.ci, hb.cout, 1, 1, false, hb.c3))) return r;
     } else {                    // upsample: cin -> cout, internal cin/4
-      hb.cin = s.a; hb.cout = s.b; hb.ci = s.a / 4;
+      hb.cin = s.cin; hb.cout = s.cout; hb.ci = s.ci;
       if ((r = fold_conv(c, ct, n + ".main_conv1.0", n + ".main_conv1.1", "", false, hb.cin, hb.cout, 1, 1, false, hb.cm))) return r;
       if ((r = fold_conv(c, ct, n + ".ext_conv1.0", n + ".ext_conv1.1", n + ".ext_conv1.2", true, hb.cin, hb.ci, 1, 1, false, hb.c1))) return r;
       if ((r = fold_conv(c, ct, n + ".ext_tconv1", n + ".ext_tconv1_bnorm", n + ".ext_tconv1_activation", true, hb.ci, hb.ci, 2, 2, true, hb.c2))) return r;
@@ -443,15 +538,18 @@ int build_host_net(bc_ctx* c, const Container& ct) {
   {
     const Tensor* w;
     int C = ct.num_classes;
-    int d[4] = {16, C, 3, 3};
+    int d[4] = {16, C, head_kernel, head_kernel};
     if ((r = need(c, ct, "transposed_conv.weight", 4, d, &w))) return r;
     int cp = C <= 16 ? 16 : 32;
     c->h_full_w.assign((size_t)9 * 16 * cp, 0.f);
+    // A 2x2 stride-2 transposed conv is the 3x3 s2 p1 op1 form with five taps zero: output (2i+qy, 2j+qx) takes
+    // input (i, j) only, which the 3x3 form reaches through taps ky = 1 + qy, kx = 1 + qx.
+    const int K = head_kernel, off = K == 3 ? 0 : 1;
     for (int k = 0; k < 16; ++k)
       for (int o = 0; o < C; ++o)
-        for (int ky = 0; ky < 3; ++ky)
-          for (int kx = 0; kx < 3; ++kx)
-            c->h_full_w[((size_t)(ky * 3 + kx) * 16 + k) * cp + o] = w->data[(((size_t)k * C + o) * 3 + ky) * 3 + kx];
+        for (int ky = 0; ky < K; ++ky)
+          for (int kx = 0; kx < K; ++kx)
+            c->h_full_w[((size_t)((ky + off) * 3 + kx + off) * 16 + k) * cp + o] = w->data[(((size_t)k * C + o) * K + ky) * K + kx];
   }
   return BC_OK;
 }
@@ -671,14 +769,14 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
     if constexpr (is16<T>::value) {
       cudaError_t ce = cudaSuccess;
       L(c, "umma_initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
-        ce = Umma<T>::launch_initial(x, kind, n, X, c->d_init_umma, c->d_init_umma_u8, c->init_u8_unscale, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
+        ce = Umma<T>::launch_initial(x, kind, n, X, c->initial_pool, c->d_init_umma, c->d_init_umma_u8, c->init_u8_unscale, c->d_lut32, c->h_init_g.data(), c->h_init_b.data(),
                                  c->h_init_a.data(), c->num_sms, s);
       });
       if (ce != cudaSuccess) return fail(c, BC_ERR_CUDA, std::string("tcgen05 initial-block launch: ") + cudaGetErrorString(ce));
     }
   } else {
     L(c, "initial", n * (131072.0 * in_px_bytes + 524288.0 * esz), n * 2.0 * 32768 * 27 * 13, s, [&] {
-      launch_initial<T>(x, kind, n, X, c->d_init_w, c->d_init_g, c->d_init_b, c->d_init_a, c->d_lut32, s);
+      launch_initial<T>(x, kind, n, X, c->initial_pool, c->d_init_w, c->d_init_g, c->d_init_b, c->d_init_a, c->d_lut32, s);
     });
   }
   int H = 128, W = 256;   // resolution of X

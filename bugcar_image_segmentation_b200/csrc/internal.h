@@ -76,7 +76,7 @@ struct BevGeom {            // kernel parameter block for K9 (passed by value)
 struct Net;   // forward (api.cu)
 
 template <typename T>
-void launch_initial(const void* x, int kind, int B, T* out, const float* w, const float* g,
+void launch_initial(const void* x, int kind, int B, T* out, int pool_kernel, const float* w, const float* g,
                     const float* b, const float* alpha, const float* lut, cudaStream_t s);
 template <typename T>
 void launch_down_a(const T* x, int B, int H, int W, int cin, int ci, T* pooled, uint8_t* idx,

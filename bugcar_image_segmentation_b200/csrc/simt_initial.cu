@@ -15,7 +15,7 @@
 namespace bc {
 
 // ------------------------------------------------------------------- initial block
-// conv3x3 s2 p1 (3->13, no bias) || maxpool3x3 s2 p1 (3) -> cat -> BN -> PReLU.
+// conv3x3 s2 p1 (3->13) || maxpool 3x3 s2 p1 (or 2x2 s2: pool2) (3) -> cat -> BN -> PReLU.
 // One thread per output pixel (128x256).  Source: uint8 BGR frame through the fp32
 // normalisation LUT (models.py:89-91 fused), or the float/double NCHW tensor
 // ENET.preprocess returns.  w: [27][13] ((c*3+ky)*3+kx major), g/b: BN scale/shift [16].
@@ -23,7 +23,7 @@ template <typename T, int KIND>
 __global__ void __launch_bounds__(128)
 k_initial(const void* __restrict__ xin, T* __restrict__ out, const float* __restrict__ w,
           const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ alpha,
-          const float* __restrict__ lut, int total) {
+          const float* __restrict__ lut, int total, int pool2) {
   __shared__ float sw[27 * 13];
   __shared__ float slut[768];
   __shared__ float sg[16], sb[16], sa[16];
@@ -63,7 +63,7 @@ k_initial(const void* __restrict__ xin, T* __restrict__ out, const float* __rest
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        mx[c] = fmaxf(mx[c], v[c]);
+        if (!pool2 || (ky > 0 && kx > 0)) mx[c] = fmaxf(mx[c], v[c]);   // 2x2 s2 pool = taps (1..2, 1..2) of the conv window
         const float* wr = sw + ((c * 3 + ky) * 3 + kx) * 13;
 #pragma unroll
         for (int o = 0; o < 13; ++o) acc[o] = fmaf(v[c], wr[o], acc[o]);
@@ -81,17 +81,18 @@ k_initial(const void* __restrict__ xin, T* __restrict__ out, const float* __rest
 }
 
 template <typename T>
-void launch_initial(const void* x, int kind, int B, T* out, const float* w, const float* g,
+void launch_initial(const void* x, int kind, int B, T* out, int pool_kernel, const float* w, const float* g,
                     const float* b, const float* alpha, const float* lut, cudaStream_t s) {
+  const int pool2 = pool_kernel == 2;
   int total = B * 128 * 256;
   int grid = (total + 127) / 128;
-  if (kind == 0) k_initial<T, 0><<<grid, 128, 0, s>>>(x, out, w, g, b, alpha, lut, total);
-  else if (kind == 1) k_initial<T, 1><<<grid, 128, 0, s>>>(x, out, w, g, b, alpha, lut, total);
-  else k_initial<T, 2><<<grid, 128, 0, s>>>(x, out, w, g, b, alpha, lut, total);
+  if (kind == 0) k_initial<T, 0><<<grid, 128, 0, s>>>(x, out, w, g, b, alpha, lut, total, pool2);
+  else if (kind == 1) k_initial<T, 1><<<grid, 128, 0, s>>>(x, out, w, g, b, alpha, lut, total, pool2);
+  else k_initial<T, 2><<<grid, 128, 0, s>>>(x, out, w, g, b, alpha, lut, total, pool2);
 }
-template void launch_initial<float>(const void*, int, int, float*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
-template void launch_initial<bf16>(const void*, int, int, bf16*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
-template void launch_initial<f16>(const void*, int, int, f16*, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
+template void launch_initial<float>(const void*, int, int, float*, int, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
+template void launch_initial<bf16>(const void*, int, int, bf16*, int, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
+template void launch_initial<f16>(const void*, int, int, f16*, int, const float*, const float*, const float*, const float*, const float*, cudaStream_t);
 
 // ------------------------------------------------------------- debug / parity export
 // NHWC activation (storage type T) -> fp32 NCHW, for per-block parity tests.

@@ -29,6 +29,7 @@ struct InitParams {
   const float* lut;          // [256][3] fp32 normalisation table (RGB order)
   float f[48];               // BN scale g[16], shift b[16], PReLU slope a[16]
   float fu8[16];             // uint8 kernel: g[o] * 2^-e(o), the un-scale of its fp16 weight limbs folded in
+  int pool2;                 // 1: the max-pool is 2x2 stride 2 (taps ky, kx in 1..2 of the conv window) instead of 3x3 s2 p1
   float fpool[6];            // uint8 kernel, pooled channels: byte -> BN(normalise(byte)) = byte * fpool[c] + fpool[3 + c]
 };
 
@@ -141,8 +142,10 @@ k_umma_initial(const __grid_constant__ InitParams p) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) v[c] = (float)s[(size_t)c * IH * IW];   // TF feed cast
             }
+            if (!p.pool2 || (ky > 0 && kx > 0)) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) mx[c] = fmaxf(mx[c], v[c]);
+              for (int c = 0; c < 3; ++c) mx[c] = fmaxf(mx[c], v[c]);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) a[(c * 3 + ky) * 3 + kx] = v[c];
@@ -325,7 +328,8 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
             make_uint4(bytes_to_h2<0, 1>(r0), bytes_to_h2<2, 3>(r0), bytes_to_h2<0, 1>(r1), bytes_to_h2<2, 3>(r1));
         // max-pool: bytes 0-2 of (r0, the window from byte 3, the window from byte 6) are the three pixels' B G R
         const uint32_t p1 = __funnelshift_r(r0, r1, 24), p2 = __funnelshift_r(r1, r2[ky], 16);
-        mx4 = __vmaxu4(mx4, __vmaxu4(r0, __vmaxu4(p1, p2)));
+        if (!p.pool2) mx4 = __vmaxu4(mx4, __vmaxu4(r0, __vmaxu4(p1, p2)));
+        else if (ky > 0) mx4 = __vmaxu4(mx4, __vmaxu4(p1, p2));        // 2x2 s2 pool: window rows / columns 1..2
       }
       // bytes 8 of the three rows, then the validity flags (1.0 = 0x3c00): only the first row / column of the
       // image has taps in the padding (2*oy + 1 <= 255 and 2*ox + 1 <= 511 always are inside)
@@ -450,7 +454,8 @@ cudaError_t Umma<act_t>::prepare_initial() {
   return e;
 }
 
-cudaError_t Umma<act_t>::launch_initial(const void* x, int kind, int B, act_t* out, const uint8_t* wblob, const uint8_t* wblob_u8,
+cudaError_t Umma<act_t>::launch_initial(const void* x, int kind, int B, act_t* out, int pool_kernel, const uint8_t* wblob,
+                                        const uint8_t* wblob_u8,
                                         const float* u8_unscale, const float* lut, const float* g, const float* b, const float* a,
                                         int num_sms, cudaStream_t s) {
   InitParams p{};
@@ -459,6 +464,7 @@ cudaError_t Umma<act_t>::launch_initial(const void* x, int kind, int B, act_t* o
   p.out = out;
   p.wblob = (kind == 0 && ((uintptr_t)x & 3) == 0) ? wblob_u8 : wblob;
   p.lut = lut;
+  p.pool2 = pool_kernel == 2;
   memcpy(p.f, g, 64);
   memcpy(p.f + 16, b, 64);
   memcpy(p.f + 32, a, 64);

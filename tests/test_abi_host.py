@@ -150,7 +150,30 @@ def test_state_dict_converter_roundtrip(tmp_path, synthetic_weights):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_weights.py"), str(src), str(dst),
                         "--classes", str(nc)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert dst.read_bytes() == blob
+    from bugcar_image_segmentation_b200 import weights as W
+    got, nc2, eps2 = W.unpack_flat(dst.read_bytes())
+    assert nc2 == nc and eps2 == eps
+    # the converter also writes the graph and the variant switches it derived (canonical graph, 3x3 pool, 3x3 head)
+    assert np.array_equal(got.pop("__graph__"), W.graph_rows()) and list(got.pop("__spec__")[:2]) == [3, 3]
+    assert list(got) == list(w) and all(np.array_equal(got[k], w[k]) for k in w)
+    assert "not part of the ENet graph" not in r.stderr           # num_batches_tracked is known noise
+
+    # bias=True checkpoints: conv biases are carried over (the loader folds them), unknown keys are reported,
+    # a non-zero bias on the class head is refused
+    sd2 = dict(sd)
+    sd2["module.regular2_1.ext_conv1.0.bias"] = torch.full((32,), 0.5)
+    sd2["module.some_aux_head.weight"] = torch.zeros(3)
+    torch.save(sd2, src)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_weights.py"), str(src), str(dst),
+                        "--classes", str(nc)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got, _, _ = W.unpack_flat(dst.read_bytes())
+    assert np.all(got["regular2_1.ext_conv1.0.bias"] == 0.5) and "some_aux_head.weight" in r.stderr
+    sd2["module.transposed_conv.bias"] = torch.ones(nc)
+    torch.save(sd2, src)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "convert_weights.py"), str(src), str(dst),
+                        "--classes", str(nc)], capture_output=True, text=True)
+    assert r.returncode != 0 and "class head" in r.stderr
 
 
 def test_laser_tables_match_oracle():

@@ -324,6 +324,14 @@ def test_bs256_distinct_frames_vs_oracle():
             ref = bev_oracle.occupancy_grid(lab[i], c["bev matrix"], ww, wh, c["cm_per_px"], 10.0, 10.0, 0.1)
             assert np.array_equal(grids[i], ref), (graphs, i)
     big.ctx.set_graphs(1)
+    # the blocking host call with sub-batch copy/compute overlap (B >= 32) AFTER the streaming call on the same
+    # context: both share the context's copy stream and events (a call order that used to hit a null event)
+    pin = torch.from_numpy(frames[:64].copy()).pin_memory()
+    out = torch.zeros((64, pipe.Hc, pipe.Wc), dtype=torch.int8).pin_memory()
+    big.ctx.pipeline_host_submit(pin, 256, 512, 64, pipe.lut, 10.0, 10.0, 0.1, 0, 0, out, None)
+    big.ctx.pipeline_host_wait(0)
+    blocking = pipe(frames[:64])
+    assert np.array_equal(out.numpy(), grids[:64]) and np.array_equal(blocking, grids[:64])
 
 
 @pytest.mark.parametrize("B", [193, 199, 211, 233, 255])

@@ -34,3 +34,27 @@ def test_torch_oracle_equals_opencv_dnn(which):
     # two engines, different summation orders: fp32 round-off, plus the rare max-pool near-tie flip downstream
     assert np.percentile(d, 99.9) <= 1e-4, np.percentile(d, 99.9)
     assert agree >= 0.9995, agree
+
+
+@pytest.mark.parametrize("variant", ["per_channel_prelu", "conv_bias_head2x2", "pool2x2_relu", "short_graph"])
+def test_variants_agree_with_opencv_dnn(variant):
+    """the variant switches of the container (weights.py __graph__ / __spec__) through both engines, 128x256 input"""
+    short = [b for b in W.ENET_BLOCKS if not b[0].startswith(("regular3", "dilated3", "asymmetric3", "dilated2_8"))]
+    kw = {"per_channel_prelu": dict(num_classes=19, prelu_per_channel=True),
+          "conv_bias_head2x2": dict(num_classes=12, conv_bias=True, head_kernel=2),
+          "pool2x2_relu": dict(num_classes=2, encoder_relu=True),
+          "short_graph": dict(num_classes=15, blocks=short)}[variant]
+    w = W.synthetic_weights(11, **kw)
+    w["__graph__"] = W.graph_rows(kw.get("blocks"))
+    w["__spec__"] = np.asarray([2 if variant == "pool2x2_relu" else 3, kw.get("head_kernel", 3), 0, 0], np.float32)
+    x = pre_oracle.preprocess(synth.noise_frame(5))[:, :, :128, :256].astype(np.float32)
+    w = enet_oracle.calibrate_bn(w, x)
+    want = enet_oracle.forward(w, x)
+    if variant != "pool2x2_relu":        # ReLU networks have exact zeros: ties in the pooling windows are legitimate there
+        assert np.array_equal(enet_onnx.forward_torch_exportable(w, x), want)
+    got = enet_onnx.forward_cv2_dnn(w, x)
+    d = np.abs(got - want) / np.abs(want).max()
+    print(f"[{variant}] cv2.dnn vs torch oracle: p99 {np.percentile(d, 99):.2e} p99.9 {np.percentile(d, 99.9):.2e} max {d.max():.2e}")
+    # fp32 round-off on 99 % of the logits; the tail is max-pool near-ties that the two engines' summation orders
+    # resolve differently (a moved activation spreads through the decoder; the short random graph smooths least)
+    assert got.shape == want.shape and np.percentile(d, 99) <= 1e-4 and np.percentile(d, 99.9) <= 5e-3

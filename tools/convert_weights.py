@@ -10,8 +10,11 @@ source tree, so:
 
   * ``.pth`` / ``.pt`` (a PyTorch ``state_dict`` of the canonical ENet, or a checkpoint holding one
     under ``state_dict``): every tensor is looked up by its parameter name and shape-checked against
-    ``weights.enet_param_spec``; ``num_batches_tracked`` and unknown keys are ignored, a missing
-    activation weight means ReLU.  Exercised by tests/test_abi_host.py.
+    ``weights.enet_param_spec``; a missing activation weight means ReLU; PReLU slopes may be shared or
+    per channel; ``<conv>.bias`` tensors (checkpoints built with bias=True) are carried over and folded
+    into the batch-norm shift by the loader, except on the class head (``transposed_conv.bias``: not
+    implemented, refused); the head kernel (3x3 or 2x2) is taken from the tensor's shape; any other
+    unknown key is reported.  Exercised by tests/test_abi_host.py.
   * ``.h5`` (Keras): pytorch2keras renames every layer to a random short name, so tensors cannot be
     matched by name.  They are matched by ORDER within each kind (conv / transposed-conv kernels, BN
     quadruples, PReLU slopes in graph order) and by shape, with kernels transposed from Keras'
@@ -34,8 +37,20 @@ def from_state_dict(sd, num_classes, encoder_relu=False, decoder_relu=True):
     if "state_dict" in sd and not any(k.endswith(".weight") for k in sd):
         sd = sd["state_dict"]
     sd = {k[7:] if k.startswith("module.") else k: v for k, v in sd.items()}
+    tc = sd.get("transposed_conv.weight")
+    head_kernel = int(tc.shape[-1]) if tc is not None and int(tc.shape[-1]) in (2, 3) else 3
+    spec = W.enet_param_spec(num_classes, encoder_relu, decoder_relu, conv_bias=True, head_kernel=head_kernel)
+    known = {n for n, _, _ in spec} | {"transposed_conv.bias"}
+    extra = sorted(k for k in sd if k not in known and not k.endswith("num_batches_tracked"))
+    if extra:
+        print(f"warning: {len(extra)} tensors of the state_dict are not part of the ENet graph and are ignored: "
+              + ", ".join(extra[:8]) + (" ..." if len(extra) > 8 else ""), file=sys.stderr)
+    if "transposed_conv.bias" in sd and np.any(np.asarray(sd["transposed_conv.bias"]) != 0):
+        raise ValueError("transposed_conv.bias is non-zero: a bias on the class head is not implemented by the loader")
     out = {}
-    for name, shape, kind in W.enet_param_spec(num_classes, encoder_relu, decoder_relu):
+    for name, shape, kind in spec:
+        if kind == "bias" and name not in sd:
+            continue                          # bias=False convolution (the canonical model)
         if name not in sd:
             if kind == "prelu":
                 continue                      # ReLU variant of this activation: no slope tensor
@@ -100,11 +115,14 @@ def main():
         import torch
         w = from_state_dict(torch.load(a.src, map_location="cpu"), a.classes)
     elif a.src.endswith(".h5"):
+        print("note: the Keras .h5 branch is EXPERIMENTAL -- it has never run (no h5py, no model.h5 in the build "
+              "container); it matches tensors by order and shape and fails on the first misfit", file=sys.stderr)
         w = from_keras_h5(a.src, a.classes)
     else:
         sys.exit("expected a .pth/.pt state_dict or a Keras .h5 file")
+    hk = int(w["transposed_conv.weight"].shape[-1])
     with open(a.dst, "wb") as f:
-        f.write(W.pack_flat(w, a.classes, a.bn_eps))
+        f.write(W.pack_flat(w, a.classes, a.bn_eps, graph=W.graph_rows(), initial_pool=3, head_kernel=hk))
     print(f"wrote {a.dst}: {len(w)} tensors, {a.classes} classes")
 
 
