@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--weights", default=WEIGHTS, choices=sorted(WEIGHT_FILES))
     ap.add_argument("--frames", default=FRAMES, choices=["scene", "noise"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--wc-staging", action="store_true", help="frame staging buffers in write-combined pinned memory (bc_host_alloc)")
     args = ap.parse_args()
     WEIGHTS, FRAMES = args.weights, args.frames
     if args.impl == "reference":
@@ -256,8 +257,16 @@ def main():
     host_sets = make_frames(rank, N_INPUT_SETS)
     if B != BATCH:
         host_sets = [s[:B] for s in host_sets]
-    pinned = [torch.from_numpy(s).pin_memory() for s in host_sets]
-    dev_sets = [p.cuda(non_blocking=True) for p in pinned]
+    if args.wc_staging:
+        from bugcar_image_segmentation_b200 import _lib
+        wc_bufs = [_lib.HostBuffer(s.shape, np.uint8, write_combined=True) for s in host_sets]
+        for b, s in zip(wc_bufs, host_sets):
+            b.array[...] = s
+        pinned = wc_bufs                                   # data_ptr() -> the C ABI takes them as they are
+        dev_sets = [torch.from_numpy(s).cuda() for s in host_sets]
+    else:
+        pinned = [torch.from_numpy(s).pin_memory() for s in host_sets]
+        dev_sets = [p.cuda(non_blocking=True) for p in pinned]
     d_grids = torch.empty((B, Hc, Wc), dtype=torch.int8, device="cuda")
     pinned_out = torch.empty((world * B if rank == 0 else B, Hc, Wc), dtype=torch.int8).pin_memory()
     stream = torch.cuda.current_stream()
@@ -340,7 +349,13 @@ def main():
     # the ceiling the end-to-end number lives under: every rank's bare pinned-host -> device copies of the same
     # frame batches, all ranks at once, nothing else running (bytes/s summed over the ranks)
     h2d_stage = torch.empty_like(dev_sets[0])
-    h2d_only = lambda i: h2d_stage.copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
+    if args.wc_staging:
+        import ctypes
+        _rt = ctypes.CDLL("libcudart.so.12")
+        h2d_only = lambda i: _rt.cudaMemcpyAsync(ctypes.c_void_p(h2d_stage.data_ptr()), ctypes.c_void_p(pinned[i % N_INPUT_SETS].data_ptr()),
+                                                 ctypes.c_size_t(B * 393216), 1, ctypes.c_void_p(stream.cuda_stream))
+    else:
+        h2d_only = lambda i: h2d_stage.copy_(pinned[i % N_INPUT_SETS], non_blocking=True)
     for i in range(3):
         h2d_only(i)
     ms_h2d = timed(h2d_only, args.steps)
@@ -566,7 +581,7 @@ def main():
                                                   "D2H by rank 0's context)"),
                     "h2d_ceiling_gbs": h2d_ceiling_gbs, "h2d_needed_gbs": e2e * 393216 / 1e9,
                     "e2e_frac_of_h2d_ceiling": e2e * 393216 / 1e9 / h2d_ceiling_gbs,
-                    "host_numa": host_bind},
+                    "host_numa": host_bind, "staging": "write-combined pinned" if args.wc_staging else "pinned"},
             "gpu_launches": int(launches), "gather_check": gather_check, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "latency_bs1": latency, "contour_filter": contour, "laserscan": laser, "config5_postprocessing": config5,
             "kernels": kernels,

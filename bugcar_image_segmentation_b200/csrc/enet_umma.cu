@@ -202,7 +202,12 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   // Service warps run their loops convergently (all 32 lanes) and elect one lane per instruction
   // inside the asm (umma_common.cuh): no divergence, no per-lane operand recomputation.
   // Descriptors advance by plain adds: the address field (bits 0-13, 16-byte units) never carries.
+  // Programmatic dependent launch: let the next kernel's CTAs start (barrier init, TMEM allocation, weight copy) as
+  // soon as SMs drain, and do not touch activations before the previous kernel has completed.  Every global
+  // access of this kernel follows from a TMA load of the producer warp, so that warp alone waits.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 0) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ============================================================ TMA producer (conv taps)
     if (full)                                            // first NX residual tiles; the rest are
       for (int k = 0; k < T && k < NX; ++k) {            // requested by the thread that frees a buffer
@@ -717,6 +722,16 @@ static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* 
   const int smem = S::TOTAL + 1024;        // opt-in set per device by prepare_bottleneck()
   const int ctas = num_sms * MINB;
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
+  static const bool pdl = getenv("BC_PDL") != nullptr && atoi(getenv("BC_PDL")) != 0;   // A/B knob, read once
+  if (pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(S::THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW>, me1, mx, my, p);
+  }
   k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }

@@ -208,11 +208,11 @@ k_umma_initial(const __grid_constant__ InitParams p) {
 static constexpr int U8_A = 128 * 128;            // A tile: 128 rows x 64 fp16 (48 used)
 static constexpr int U8_W = 16 * 128;             // one limb of B: 16 rows x 64 fp16
 static constexpr int U8_K = 48;
-static constexpr int U8_OFF_A = 0;                // two A tiles: tile k+1 is built while the MMAs of tile k run
-static constexpr int U8_OFF_W = 2 * U8_A;
+static constexpr int U8_OFF_A = 0;
+static constexpr int U8_OFF_W = U8_A;
 static constexpr int U8_OFF_BAR = U8_OFF_W + 3 * U8_W;
 static constexpr int U8_SMEM = U8_OFF_BAR + 64;
-static constexpr int U8_MINB = 5;
+static constexpr int U8_MINB = 7;    // (a second A tile so that tile k+1 is built during tile k's MMAs, 5 CTAs/SM, measured 160 vs 150 us)
 
 // K index of window byte b (0..8) of row ky, and of the validity flag of tap (ky, kx)
 __host__ __device__ constexpr int u8_k_byte(int ky, int b) { return b < 8 ? ky * 8 + b : 24 + ky; }
@@ -232,16 +232,14 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bars = (uint64_t*)(smem + U8_OFF_BAR);
-  enum { A_FULL0 = 0, A_FULL1, D_FULL0, D_FULL1, W_FULL, NBARS };
+  enum { A_FULL0 = 0, D_FULL0, W_FULL, NBARS };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(bar(A_FULL0), 128);
-    mbar_init(bar(A_FULL1), 128);
     mbar_init(bar(D_FULL0), 1);
-    mbar_init(bar(D_FULL1), 1);
     mbar_init(bar(W_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(bar(W_FULL), 3 * U8_W);
@@ -251,13 +249,11 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   } else {
-    // K columns 40..63 of this thread's A rows are never written again: zero them once
+    // K columns 40..63 of this thread's A row are never written again: zero them once
     const int m = (warp & 3) * 32 + lane;
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int j = 5; j < 8; ++j)
-        *reinterpret_cast<uint4*>(smem + U8_OFF_A + b * U8_A + swz<128>((uint32_t)(m * 128 + j * 16))) = make_uint4(0u, 0u, 0u, 0u);
+    for (int j = 5; j < 8; ++j)
+      *reinterpret_cast<uint4*>(smem + U8_OFF_A + swz<128>((uint32_t)(m * 128 + j * 16))) = make_uint4(0u, 0u, 0u, 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -271,17 +267,15 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     constexpr uint32_t IDESC = instr_desc_fmt(128, 16, 0u);       // fp16 bytes x fp16 weight limbs, whatever act_t is
     mbar_wait(bar(W_FULL), 0);
     for (int k = 0; k < T; ++k) {
-      const int b = k & 1;
-      // A_FULL(k) also says that accumulator b is free: every thread read tile k-2's result before it built tile k
-      mbar_wait(bar(A_FULL0 + b), (k >> 1) & 1);
+      // A_FULL(k) also says that the accumulator is free: every thread read tile k-1's result before it built tile k
+      mbar_wait(bar(A_FULL0), k & 1);
       tc_fence_after();
 #pragma unroll
       for (int limb = 0; limb < 3; ++limb)
 #pragma unroll
         for (int kk = 0; kk < U8_K / 16; ++kk)
-          umma_mma_e(tmem + b * 16, dA0 + (uint64_t)(b * (U8_A >> 4) + kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2),
-                     IDESC, (limb | kk) != 0);
-      umma_commit_e(bar(D_FULL0 + b));
+          umma_mma_e(tmem, dA0 + (uint64_t)(kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2), IDESC, (limb | kk) != 0);
+      umma_commit_e(bar(D_FULL0));
     }
   } else {
     const int q4 = warp & 3;
@@ -291,9 +285,8 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     // 6*ox - 3 of the row: fetched as the three aligned 32-bit words that cover them, realigned with
     // funnel shifts.  ox = 0: the first word would lie before the row; its bytes are padding anyway.
     // Words of rows outside the image stay zero, so every padding tap is a zero byte.
-    // Software pipeline per thread: the words of tile k+2 are requested, then the A row of tile k+1 is built
-    // (second A buffer) and handed to the MMA warp, and only then does the thread wait for tile k's
-    // accumulator: global-load latency and the MMA round trip both hide behind useful work.
+    // The words of tile k+1 are requested before this thread waits for tile k's accumulator, so the global-load
+    // latency hides behind the MMA round trip (the other resident CTAs hide the round trip itself).
     uint32_t w[9];
     int pix = 0, ox = 0, oy = 0;
     auto fetch = [&](int k) {
@@ -314,9 +307,9 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
         }
       }
     };
-    // builds the A row of the tile whose words are in w[] into buffer b; returns the packed max-pool bytes (B, G, R)
-    auto build = [&](int b) -> uint32_t {
-      uint8_t* A = smem + U8_OFF_A + b * U8_A;
+    // builds the A row of the tile whose words are in w[]; returns the packed max-pool bytes (B, G, R)
+    auto build = [&]() -> uint32_t {
+      uint8_t* A = smem + U8_OFF_A;
       const int sh = ((6 * ox - 3) & 3) * 8;            // 8 or 24
       uint32_t r2[3], mx4 = 0u;
 #pragma unroll
@@ -338,30 +331,22 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 3 * 16))) = make_uint4(b8a, b8b, vtl | (vt << 16), vt | (vl << 16));
       *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 4 * 16))) = make_uint4(0x3c003c00u, vl | (0x3c00u << 16), 0x3c00u, 0u);
       fence_proxy_async();
-      mbar_arrive(bar(A_FULL0 + b));
+      mbar_arrive(bar(A_FULL0));
       return mx4;
     };
-    uint32_t mx_cur = 0u, mx_next = 0u;
-    int pix_cur = 0, pix_next = 0;
-    if (T > 0) {
-      fetch(0);
-      pix_cur = pix;
-      mx_cur = build(0);
-      if (T > 1) fetch(1);
-    }
+    if (T > 0) fetch(0);
     for (int k = 0; k < T; ++k) {
-      if (k + 1 < T) {                                  // tile k+1: its words arrived while tile k-1 was finished
-        pix_next = pix;
-        mx_next = build((k + 1) & 1);                   // (the MMAs of tile k-1 have finished reading that buffer: D_FULL(k-1) was waited for)
-        if (k + 2 < T) fetch(k + 2);
-      }
+      // (the MMAs of tile k-1 have finished reading A: this thread passed its D_FULL wait below)
+      const int pix_cur = pix;
+      const uint32_t mx_cur = build();
+      if (k + 1 < T) fetch(k + 1);
       // ---- epilogue of tile k: BN (with the weights' power-of-two un-scale folded in) + PReLU on the 13 conv
       // channels; the 3 pooled channels: max-pool of the normalised image = normalisation of the max byte (the
       // map is increasing), and normalisation + BN are one affine map of the byte (host-folded, fpool)
-      mbar_wait(bar(D_FULL0 + (k & 1)), (k >> 1) & 1);
+      mbar_wait(bar(D_FULL0), k & 1);
       tc_fence_after();
       float r[16];
-      tmem_ld16(tm_lane + (k & 1) * 16, r);
+      tmem_ld16(tm_lane, r);
       tc_fence_before();
 #pragma unroll
       for (int o = 0; o < 13; ++o) r[o] = prelu_f(fmaf(r[o], p.fu8[o], p.f[16 + o]), p.f[32 + o]);
@@ -371,8 +356,6 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix_cur * 16);
       o[0] = pack8(r);
       o[1] = pack8(r + 8);
-      mx_cur = mx_next;
-      pix_cur = pix_next;
     }
   }
   tc_fence_before();

@@ -96,7 +96,12 @@ traffic.update(capture(os.path.join(G, f"{rnd}_step_light.ncu-rep"), os.path.joi
                        "--clock-control none python tools/prof_run.py 256 1\n# (one pipeline step, bs 256, B200; per-launch averages; "
                        "stall sites below from --set full captures of one launch each)",
                        stall_reps=((os.path.join(G, f"{rnd}_b128_full.ncu-rep"), "k_umma_bottleneck<128, 32, 32, 128, 2, 1"),
-                                   (os.path.join(G, f"{rnd}_b64_full.ncu-rep"), "k_umma_bottleneck<64, 16, 16, 64"))))
+                                   (os.path.join(G, f"{rnd}_b64_full.ncu-rep"), "k_umma_bottleneck<64, 16, 16, 64"),
+                                   (os.path.join(G, f"{rnd}_init_full.ncu-rep"), "k_umma_initial_u8"),
+                                   (os.path.join(G, f"{rnd}_head_full.ncu-rep"), "k_umma_head"),
+                                   (os.path.join(G, f"{rnd}_up4_full.ncu-rep"), "k_umma_up<128"),
+                                   (os.path.join(G, f"{rnd}_s5_full.ncu-rep"), "k_stage5"),
+                                   (os.path.join(G, f"{rnd}_occ_full.ncu-rep"), "k_occgrid"))))
 traffic.update(capture(os.path.join(G, f"{rnd}_contour_full.ncu-rep"), os.path.join(P, f"{rnd}_contour_ncu.txt"),
                        "# ncu --set full --clock-control none -k regex:k_cn python tools/bench_contour.py  (256 masks of 256x512, B200)"))
 if traffic:
