@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbugcar_b200.so")
+LIB_PATH = os.environ.get("BUGCAR_B200_LIB") or os.path.join(_HERE, "libbugcar_b200.so")     # override: A/B builds
 
 BC_OK, BC_ERR_ARG, BC_ERR_STATE, BC_ERR_CUDA, BC_ERR_FORMAT, BC_ERR_NOMEM = 0, -1, -2, -3, -4, -5
 BC_IN_BGR_U8, BC_IN_NCHW_F32, BC_IN_NCHW_F64 = 0, 1, 2
