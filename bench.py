@@ -128,7 +128,7 @@ def make_frames(rank, n_sets):
 BLOCKIO_BYTES_PER_FRAME = {
     "umma_initial": 393216 + 1048576, "umma_pool_conv16": 0, "umma_down64": 1048576 + 1048576 + 131072,
     "umma_bottleneck64": 2097152, "umma_pool_conv64": 0, "umma_down128": 1048576 + 524288 + 131072,
-    "umma_bottleneck128": 1048576, "umma_conv5x1": 0, "umma_bottleneck128_asym": 1048576,
+    "umma_bottleneck128": 1048576, "umma_conv5x1": 0, "umma_bottleneck128_asym": 1048576, "umma_asym_fused": 1048576,
     "umma_up4": 524288 + 1048576 + 131072, "umma_up5": 1048576 + 1048576 + 131072, "stage5_bottleneck": 2097152,
     "umma_head_argmax_lut": 1048576 + 131072, "occgrid": 131072 + 10000,
 }

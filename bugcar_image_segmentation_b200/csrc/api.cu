@@ -556,7 +556,7 @@ int build_host_net(bc_ctx* c, const Container& ct) {
 
 // ------------------------------------------------------------------- device upload
 void free_net(bc_ctx* c) {
-  for (Bottleneck& b : c->blocks) { umma_free(b.um_a); umma_free(b.um_b); }
+  for (Bottleneck& b : c->blocks) { umma_free(b.um_a); umma_free(b.um_b); umma_free(b.um_f); }
   for (void* p : c->dev_allocs) cudaFree(p);
   if (c->d_head_umma) cudaFree(c->d_head_umma);
   if (c->d_init_umma) cudaFree(c->d_init_umma);
@@ -652,7 +652,10 @@ int build_umma_packs(bc_ctx* c) {
         ok = U::build(b.um_a, b.cin, b.ci, b.ci, b.cin, hb.c2.w.data(), 5, hb.c2.bias.data(), hb.c2.alpha.data(), nullptr, nullptr,
                         nullptr, nullptr, nullptr, nullptr, nullptr) &&
              U::build(b.um_b, b.cin, b.ci, b.ci, b.cin, hb.c2b.w.data(), 5, hb.c2b.bias.data(), hb.c2b.alpha.data(), hb.c3.w.data(),
-                        hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na);
+                        hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na) &&
+             (b.cin != 128 ||        // the one-kernel form of the block (128 channels)
+              U::build_asym(b.um_f, hb.c2.w.data(), hb.c2.bias.data(), hb.c2.alpha.data(), hb.c2b.w.data(), hb.c2b.bias.data(),
+                            hb.c2b.alpha.data(), hb.c3.w.data(), hb.c3.bias.data(), hb.c3.alpha.data(), hb.alpha_out.data(), nw, nb, na));
       }
       if (!ok) return fail(c, BC_ERR_CUDA, "building the tcgen05 operand packs failed");
     }
@@ -785,7 +788,7 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
   // direction in which the tensor now in X was written; the next kernel walks the other way.  Every kernel
   // after the initial block can walk backwards; the CUDA-core fall-backs (fp32 mode, tensor cores off) ignore
   // the flag, which only costs the L2 hits
-  static const bool snake = getenv("BC_NO_SNAKE") == nullptr;
+  static const bool snake = getenv("BC_NO_SNAKE") == nullptr, asym_fusion = getenv("BC_NO_ASYM_FUSION") == nullptr;
   int x_dir = 0;
   auto flip_dir = [&]() { x_dir = snake ? !x_dir : 0; g_umma_reverse = x_dir; };
   bool e1_ready = false;    // E1 already holds this block's projection (written by the previous tcgen05 kernel)
@@ -842,6 +845,11 @@ int forward_chunk(bc_ctx* c, const void* x, int kind, int n, float* logits, uint
             L(c, b.cin == 64 ? "umma_bottleneck64" : "umma_bottleneck128", io,
               2.0 * px * (9.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
               [&] { ce = Umma<T>::launch(b.um_a, E1, X, Y, E2, n, H, W, taps_for(3, 3, b.dilation), 0, has_next, c->num_sms, s); });
+            std::swap(E1, E2);        // e1' of the next block was written to E2
+          } else if (b.um_f.wblob && W == 64 && asym_fusion) {
+            // the whole asymmetric block in one launch: the 5x1 result stays in shared memory
+            L(c, "umma_asym_fused", io, 2.0 * px * (10.0 * b.ci * b.ci + b.ci * b.cin * (1 + has_next)), s,
+              [&] { ce = Umma<T>::launch_asym(b.um_f, E1, X, Y, E2, n, H, W, taps_for(5, 1, 1), has_next, c->num_sms, s); });
             std::swap(E1, E2);        // e1' of the next block was written to E2
           } else {
             L(c, "umma_conv5x1", px * 2.0 * b.ci * esz, 2.0 * px * 5.0 * b.ci * b.ci, s,

@@ -52,11 +52,12 @@ struct UmmaParams {
   // fp32 bias / PReLU-slope block b2[CI] a2[CI] b3[C] a3[C] aout[C] b1n[CN] a1n[CN], by value: the
   // epilogues index it with compile-time channel numbers, so every use is a constant-bank operand
   // of the FADD / FMUL itself (no load instruction, no shared-memory traffic)
-  float f[512];
+  // fused asymmetric block: + b0[CI] a0[CI] of the 5x1 conv at the end
+  float f[576];
 };
 
 // weight image (identical in global and shared memory): offsets relative to its start
-template <int C, int CI, int CN>
+template <int C, int CI, int CN, int NT = 9>
 struct UmmaWeights {
   static constexpr int RB = CI * 2;                 // row bytes of the CI-wide operands (64 / 32)
   static constexpr int W2_TAP = CI * RB;            // one tap of W2: [CI out][CI in]
@@ -64,23 +65,29 @@ struct UmmaWeights {
   static constexpr int NSUB = C / 64;
   static constexpr int W1_SUB = CN * 128;           // [CN out][64 in] sub-tile of the next projection
   static constexpr int OFF_W2 = 0;
-  static constexpr int OFF_W3 = 9 * W2_TAP;
-  static constexpr int OFF_W1 = ((9 * W2_TAP + W3_BYTES + 1023) / 1024) * 1024;   // 128-byte swizzle: 1 KB aligned
+  static constexpr int OFF_W3 = NT * W2_TAP;
+  static constexpr int OFF_W1 = ((NT * W2_TAP + W3_BYTES + 1023) / 1024) * 1024;   // 128-byte swizzle: 1 KB aligned
   static constexpr int W_BYTES = OFF_W1 + NSUB * W1_SUB;
-  static constexpr int NF = 2 * CI + 3 * C + 2 * CN;   // fp32 parameter block
+  static constexpr int NF = 2 * CI + 3 * C + 2 * CN + (NT == 10 ? 2 * CI : 0);   // fp32 parameter block
 };
 
 // CN = width of the next block's projection, CRES = residual channels (C: regular bottleneck,
 // < C: down-sampling bottleneck), NG = epilogue groups per CTA (tiles in flight), MINB = CTAs per SM
 // CONV: conv-only specialisation (first half of an asymmetric bottleneck: taps -> e2 in global memory);
 // no residual / y tiles, no e2 tile, only the conv weights: small enough for two CTAs per SM
-template <int C, int CI, int CN, int CRES, int NG_, int MINB_, bool CONV = false, int EPW_ = 1>
+// ASYM: the whole asymmetric block in one kernel: 5x1 conv (vertical slab from the ring) -> D0 -> epilogue 0 writes the
+// result as a PIXEL-INTERLEAVED slab into shared memory -> 1x5 conv through shifted descriptors on that slab -> D1 ->
+// the usual chain.  The intermediate tensor never leaves the SM and one launch per block disappears.
+template <int C, int CI, int CN, int CRES, int NG_, int MINB_, bool CONV = false, int EPW_ = 1, bool ASYM_ = false>
 struct UmmaSmem {
-  using Wt = UmmaWeights<C, CI, CN>;
+  static constexpr bool ASYM = ASYM_;
+  using Wt = UmmaWeights<C, CI, CN, ASYM_ ? 10 : 9>;
+  static constexpr int SERVICE = ASYM ? 8 : 4;      // service warps (ASYM: a second conv issuer; padded to a multiple of four so that
+                                                    // an epilogue warp's index mod 4 stays its TMEM lane quarter)
   static constexpr int NG = NG_, MINB = MINB_;
   static constexpr bool NARROW = CRES < C;
   static constexpr int EPW = EPW_;                  // warps per TMEM lane quarter of an epilogue group
-  static constexpr int THREADS = 128 + 128 * NG * EPW;
+  static constexpr int THREADS = 32 * SERVICE + 128 * NG * EPW;
   static constexpr int RB = CI * 2;
   static constexpr int TAP_BYTES = 128 * RB;        // one A tap tile
   // ring slot: a tap tile, or (row-slab mode, CI = 16) one image row of 128 + 2 pixels, padded to the 32-byte-swizzle repeat
@@ -109,22 +116,29 @@ struct UmmaSmem {
   static constexpr int OFF_R = OFF_X + NY * XBUF;
   static constexpr int OFF_TAPS = OFF_R + NX * RBUF;
   static constexpr int OFF_E2 = ((OFF_TAPS + RING_BYTES + 1023) / 1024) * 1024;   // one e2 tile per group
-  static constexpr int OFF_W = OFF_E2 + (CONV ? 0 : NG) * TAP_BYTES;  // weight image starts here
+  // ASYM: the group's slab of the 5x1 result, [64 + 4 px][2 rows][CI] = 8 704 B, shares its memory with the e2 tile (the
+  // 1x5 MMAs have consumed the slab before epilogue 1 writes e2)
+  static constexpr int PS_BYTES = 68 * 2 * RB;
+  static constexpr int E2_STRIDE = ASYM ? ((PS_BYTES + 1023) / 1024) * 1024 : TAP_BYTES;
+  static constexpr int OFF_W = OFF_E2 + (CONV ? 0 : NG) * E2_STRIDE;  // weight image starts here
   static constexpr int OFF_W2 = OFF_W + Wt::OFF_W2, OFF_W3 = OFF_W + Wt::OFF_W3, OFF_W1 = OFF_W + Wt::OFF_W1;
   static constexpr int W_LOAD = CONV ? 9 * Wt::W2_TAP : Wt::W_BYTES;  // bytes of the weight image this kernel needs
+  static_assert(!ASYM || (!CONV && !NARROW && CI == 32), "fused asymmetric block: full 128-channel form only");
   static constexpr int OFF_BAR = OFF_W + ((W_LOAD + 1023) / 1024) * 1024;
   static constexpr int TOTAL = OFF_BAR + 1024;
   // barriers
   static constexpr int X_FULL = 0, D1_FULL = X_FULL + NX, D1_EMPTY = D1_FULL + NG,
                        E2_FULL = D1_EMPTY + NG, D2_FULL = E2_FULL + NG, Y_FULL = D2_FULL + NG, D3_FULL = Y_FULL + NG,
                        D3_EMPTY = D3_FULL + NG, W_FULL = D3_EMPTY + NG, TAP_FULL = W_FULL + 1, TAP_EMPTY = TAP_FULL + NRING,
-                       NBARS = TAP_EMPTY + NRING;
+                       D0_FULL = TAP_EMPTY + NRING, D0_EMPTY = D0_FULL + NG, PS_FULL = D0_EMPTY + NG,
+                       NBARS = PS_FULL + NG;
   static_assert(NBARS * 8 + 8 + 4 * NX <= 1024, "barrier block");
   // 227 KB per CTA, 228 KB per SM with 1 KB reserved per resident CTA; + 1 KB alignment slack
   static_assert(TOTAL + 1024 <= 232448 && (TOTAL + 2048) * MINB <= 233472, "shared memory budget");
   // TMEM columns: every group owns a D1 / D2 / D3 accumulator
   static constexpr uint32_t COL_D1 = 0, COL_D2 = NG * CI, COL_D3 = ALIAS13 ? COL_D1 : NG * (CI + C);
-  static constexpr uint32_t COLS_USED = CONV ? NG * CI : ALIAS13 ? NG * (CI + C) : NG * (CI + C + CN);
+  static constexpr uint32_t COL_D0 = NG * (CI + C + CN);              // ASYM: accumulator of the 5x1 conv
+  static constexpr uint32_t COLS_USED = CONV ? NG * CI : ALIAS13 ? NG * (CI + C) : NG * (CI + C + CN) + (ASYM ? NG * CI : 0);
   static_assert(!ALIAS13 || CN == CI, "D3 reuses D1's columns");
   static constexpr uint32_t TMEM_COLS = COLS_USED <= 32 ? 32 : COLS_USED <= 64 ? 64 : COLS_USED <= 128 ? 128
                                         : COLS_USED <= 256 ? 256 : 512;
@@ -144,15 +158,15 @@ struct UmmaSmem {
 //   warps 4.. epilogue       group g = (warp - 4) / 4; one TMEM lane (= pixel) per thread:
 //                            D1 -> e2 (smem), D2 + x -> y (smem, TMA store), D3 -> e1' (global);
 //                            its first thread stores y and requests the x tile that reuses the buffer
-template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false, int EPW = 1>
-__global__ void __launch_bounds__(128 + 128 * NG * EPW, MINB)
+template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false, int EPW = 1, bool ASYM = false>
+__global__ void __launch_bounds__((ASYM ? 256 : 128) + 128 * NG * EPW, MINB)
 k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][CI], box = one tile, swizzle RB
                   const __grid_constant__ CUtensorMap map_x,    // 2D [pixels][C], box [128 px][64 ch], swizzle 128
                                                                 // (narrow: [pixels][CRES], box [128 px][CRES])
                   const __grid_constant__ CUtensorMap map_y,    // same shape, the output
                   const __grid_constant__ UmmaParams p) {
-  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV, EPW>;
-  using Wt = UmmaWeights<C, CI, CN>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV, EPW, ASYM>;
+  using Wt = typename S::Wt;
   constexpr int RB = S::RB;
   constexpr int NX = S::NX;
   constexpr bool NARROW = S::NARROW;
@@ -161,7 +175,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer: LDS/STS, not generic LD/ST
   const uint32_t sbase = smem_u32(smem);
   constexpr int F_B2 = 0, F_A2 = CI, F_B3 = 2 * CI, F_A3 = F_B3 + C, F_AOUT = F_A3 + C, F_B1N = F_AOUT + C, F_A1N = F_B1N + CN;
-  static_assert(F_A1N + CN <= 512, "parameter block");
+  constexpr int F_B0 = F_A1N + CN, F_A0 = F_B0 + CI;        // ASYM: bias / slope of the 5x1 conv
+  static_assert(F_A1N + CN + (ASYM ? 2 * CI : 0) <= 576, "parameter block");
   uint64_t* bars = (uint64_t*)(smem + S::OFF_BAR);
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[S::NBARS];
@@ -173,7 +188,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     for (int i = 0; i < S::NBARS; ++i) {
       // D1_EMPTY / E2_FULL / Y_FULL: every thread of the group arrives; the rest: one arrival
       const bool by_group = (i >= S::D1_EMPTY && i < S::D1_EMPTY + NG) || (i >= S::E2_FULL && i < S::E2_FULL + NG) ||
-                            (i >= S::Y_FULL && i < S::Y_FULL + NG) || (i >= S::D3_EMPTY && i < S::D3_EMPTY + NG);
+                            (i >= S::Y_FULL && i < S::Y_FULL + NG) || (i >= S::D3_EMPTY && i < S::D3_EMPTY + NG) ||
+                            (i >= S::D0_EMPTY && i < S::D0_EMPTY + NG) || (i >= S::PS_FULL && i < S::PS_FULL + NG);
       mbar_init(bar(i), by_group ? 128 * EPW : 1);
     }
     for (int i = 0; i < NX; ++i) xfills[i] = 0u;
@@ -184,6 +200,15 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(S::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if constexpr (ASYM) {
+    // zero columns of the 5x1-result slabs (2 pixels left and right of the 64: slab rows 0-3 and 132-135); the right
+    // ones are never written again, the left ones are re-zeroed by epilogue 0 (the e2 tile shares their memory)
+    for (int i = tid; i < NG * 32; i += S::THREADS) {
+      const int g = i >> 5, c = i & 31;
+      *reinterpret_cast<uint4*>(smem + S::OFF_E2 + g * S::E2_STRIDE + (c < 16 ? c * 16 : 132 * RB + (c - 16) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -276,12 +301,15 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   } else if (warp == 1) {
     // ============================================================ MMA issuer: conv taps -> D1[group]
     const uint64_t dA0 = smem_desc<RB>(sbase + S::OFF_TAPS), dB0 = smem_desc<RB>(sbase + S::OFF_W2);
+    // the conv fed from the tap ring accumulates into D1 -- or, in the fused asymmetric block, into D0 (5x1 half)
+    constexpr uint32_t COL_C = ASYM ? S::COL_D0 : S::COL_D1;
+    constexpr int C_FULL = ASYM ? S::D0_FULL : S::D1_FULL, C_EMPTY = ASYM ? S::D0_EMPTY : S::D1_EMPTY;
     int slot = 0, round = 0;
     mbar_wait(bar(S::W_FULL), 0);
     for (int k = 0; k < T; ++k) {
       const int g = k % NG;
       if (k >= NG) {
-        mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+        mbar_wait(bar(C_EMPTY + g), ((k / NG) - 1) & 1);
         if (S::ALIAS13 && p.has_next) mbar_wait(bar(S::D3_EMPTY + g), ((k / NG) - 1) & 1);   // D3 of the group's previous tile lives in D1's columns
       }
       if (CI == 32 && p.vslab) {
@@ -291,7 +319,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         for (int ky = 0; ky < 5; ++ky)                    // one image row = 64 pixels x 64 bytes = 8 swizzle atoms
 #pragma unroll
           for (int kk = 0; kk < CI / 16; ++kk)
-            umma_mma_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + ky * 256 + kk * 2),
+            umma_mma_e(tmem + COL_C + g * CI, dA0 + (uint64_t)(slot * (S::SLOT_BYTES >> 4) + ky * 256 + kk * 2),
                         dB0 + (uint64_t)(ky * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (ky | kk) != 0);
         umma_commit_e(bar(S::TAP_EMPTY + slot));
         slot += 3;
@@ -332,6 +360,24 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         umma_commit_e(bar(S::TAP_EMPTY + slot));          // slot reusable once these MMAs retire
         if (++slot == S::NRING) { slot = 0; ++round; }
       }
+      umma_commit_e(bar(C_FULL + g));
+    }
+  } else if (ASYM && warp == 4) {
+    // ============================================================ MMA issuer (fused asymmetric block): 1x5 conv on the
+    // group's slab of the 5x1 result -> D1[group]; kernel column kx = the slab read kx pixels (128 bytes) in
+    const uint64_t dA0 = smem_desc<RB>(sbase + S::OFF_E2), dB0 = smem_desc<RB>(sbase + S::OFF_W2 + 5 * Wt::W2_TAP);
+    mbar_wait(bar(S::W_FULL), 0);
+    for (int k = 0; k < T; ++k) {
+      const int g = k % NG;
+      mbar_wait(bar(S::PS_FULL + g), (k / NG) & 1);
+      if (k >= NG) mbar_wait(bar(S::D1_EMPTY + g), ((k / NG) - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+        for (int kk = 0; kk < CI / 16; ++kk)
+          umma_mma_e(tmem + S::COL_D1 + g * CI, dA0 + (uint64_t)(g * (S::E2_STRIDE >> 4) + kx * (2 * RB >> 4) + kk * 2),
+                     dB0 + (uint64_t)(kx * (Wt::W2_TAP >> 4) + kk * 2), IDESC_CONV, (kx | kk) != 0);
       umma_commit_e(bar(S::D1_FULL + g));
     }
   } else if (warp == 2) {
@@ -345,7 +391,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < CI / 16; ++kk)
-          umma_mma_e(tmem + S::COL_D2 + g * C, dA0 + (uint64_t)(g * (S::TAP_BYTES >> 4) + kk * 2), dB0 + (uint64_t)(kk * 2),
+          umma_mma_e(tmem + S::COL_D2 + g * C, dA0 + (uint64_t)(g * (S::E2_STRIDE >> 4) + kk * 2), dB0 + (uint64_t)(kk * 2),
                       IDESC_EXP, kk != 0);
         umma_commit_e(bar(S::D2_FULL + g));
       }
@@ -367,50 +413,85 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         umma_commit_e(bar(S::D3_FULL + g));
       }
     }
-  } else {
-    // ============================================================ epilogue (warps 4..)
+  } else if (warp >= S::SERVICE) {
+    // ============================================================ epilogue (warps 4.., or 8.. in the fused asymmetric block)
     // EPW warps share a TMEM lane quarter of a group: warp-half eh takes 1 / EPW of the columns of every
     // epilogue (compile-time halves, so the biases and slopes stay constant-bank operands)
-    const int grp = (warp - 4) / (4 * EPW);  // epilogue group = tile slot
+    const int grp = (warp - S::SERVICE) / (4 * EPW);  // epilogue group = tile slot
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;             // row of the tile = TMEM lane
     // the tile's pixel (in memory order) this lane holds: itself, or in pair-slab mode (row m % 2, column m / 2)
     const int mp = (CI == 32 && !CONV && p.pairslab) ? ((m & 1) << 6) | (m >> 1) : m;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
-    uint8_t* e2buf = smem + S::OFF_E2 + grp * S::TAP_BYTES;
+    uint8_t* e2buf = smem + S::OFF_E2 + grp * S::E2_STRIDE;
     mbar_wait(bar(S::W_FULL), 0);
     auto run = [&](auto HH) {
     constexpr int EH = decltype(HH)::value;
     constexpr int CI1 = CI / EPW, C1 = C / EPW, CN1 = CN / EPW;     // this warp's share of the columns
     static_assert(CI1 % 16 == 0 && CN1 % 16 == 0 && C1 % 32 == 0, "column split");
     const bool storer = (q == 0 && EH == 0 && lane == 0);
-    for (int k = grp; k < T; k += NG) {
-      const int tile = tile_of(k);
-      const uint32_t par = (uint32_t)(k / NG) & 1;
-      // ---- epilogue 1: +bias, PReLU, 16-bit -> e2 tile (A operand of the expansion) or global
-      {
-        float v[CI1];
-        mbar_wait(bar(S::D1_FULL + grp), par);
+    // ---- epilogue 0 (fused asymmetric block): 5x1 result + bias, PReLU, 16-bit -> the group's slab.  D0's lanes
+    // are in image order (lane m = row m / 64, column m % 64: the vertical-slab conv); the slab is pixel-interleaved
+    // [column + 2][row], which is what gives D1 the pair order the later epilogues assume
+    auto ep0 = [&](int k) {
+      if constexpr (ASYM) {
+        static_assert(!ASYM || EPW == 1, "fused asymmetric block: one warp per lane quarter");
+        float v[CI];
+        mbar_wait(bar(S::D0_FULL + grp), (uint32_t)(k / NG) & 1);
         tc_fence_after();
-        if constexpr (CI1 == 32) tmem_ld32(tm_lane + S::COL_D1 + grp * CI + EH * CI1, v);
-        else tmem_ld16(tm_lane + S::COL_D1 + grp * CI + EH * CI1, v);
+        tmem_ld32(tm_lane + S::COL_D0 + grp * CI, v);
         tc_fence_before();
-        mbar_arrive(bar(S::D1_EMPTY + grp));
+        mbar_arrive(bar(S::D0_EMPTY + grp));
 #pragma unroll
-        for (int j = 0; j < CI1; ++j) v[j] = prelu_f(v[j] + p.f[F_B2 + EH * CI1 + j], p.f[F_A2 + EH * CI1 + j]);
-        if constexpr (!full) {
-          uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CI + EH * CI1);
+        for (int j = 0; j < CI; ++j) v[j] = prelu_f(v[j] + p.f[F_B0 + j], p.f[F_A0 + j]);
+        const int pos = (((m & 63) + 2) << 1) | (m >> 6);          // slab row of this pixel
 #pragma unroll
-          for (int c = 0; c < CI1 / 8; ++c)
-            o[c] = pack8(v + 8 * c);
-          continue;
-        }
+        for (int c = 0; c < CI / 8; ++c)
+          *reinterpret_cast<uint4*>(e2buf + swz<RB>(pos * RB + c * 16)) = pack8(v + 8 * c);
+        if (m < 16) *reinterpret_cast<uint4*>(e2buf + m * 16) = make_uint4(0u, 0u, 0u, 0u);   // left zero columns (the previous e2 tile lay over them)
+        fence_proxy_async();
+        mbar_arrive(bar(S::PS_FULL + grp));
+      }
+    };
+    // ---- epilogue 1: +bias, PReLU, 16-bit -> e2 tile (A operand of the expansion) or global
+    auto ep1 = [&](int k) {
+      float v[CI1];
+      mbar_wait(bar(S::D1_FULL + grp), (uint32_t)(k / NG) & 1);
+      tc_fence_after();
+      if constexpr (CI1 == 32) tmem_ld32(tm_lane + S::COL_D1 + grp * CI + EH * CI1, v);
+      else tmem_ld16(tm_lane + S::COL_D1 + grp * CI + EH * CI1, v);
+      tc_fence_before();
+      mbar_arrive(bar(S::D1_EMPTY + grp));
+#pragma unroll
+      for (int j = 0; j < CI1; ++j) v[j] = prelu_f(v[j] + p.f[F_B2 + EH * CI1 + j], p.f[F_A2 + EH * CI1 + j]);
+      if constexpr (!full) {
+        uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile_of(k) * 128 + m) * CI + EH * CI1);
+#pragma unroll
+        for (int c = 0; c < CI1 / 8; ++c)
+          o[c] = pack8(v + 8 * c);
+      } else {
 #pragma unroll
         for (int c = 0; c < CI1 / 8; ++c)
           *reinterpret_cast<uint4*>(e2buf + swz<RB>(m * RB + (EH * CI1 / 8 + c) * 16)) = pack8(v + 8 * c);
         fence_proxy_async();
         mbar_arrive(bar(S::E2_FULL + grp));
       }
+    };
+    // The chain of a tile is  [ep0 | 1x5 MMAs] ep1 | expansion MMAs | ep2 | projection MMAs | ep3, and the group idles
+    // through every MMA round trip (arrive -> issuer wakes -> MMAs -> commit -> waiters wake, ~600 cycles each).  In the
+    // fused asymmetric block the extra stage is hidden by software pipelining: ep0(k + NG) runs right after ep2(k),
+    // while tile k's projection MMAs run, and the next tile's 1x5 MMAs run under ep3(k) (82 -> 77 us per launch; the
+    // slab is free: the MMAs that read it finished before the D1 / D2 barriers this group has passed).  Pulling ep1
+    // forward the same way in the ordinary blocks was measured SLOWER (65 -> 69 us: the issuer warps serve the groups
+    // in tile order, and the later ep3 delays the residual buffer's refill), so they keep program order.
+    if constexpr (ASYM) {
+      if (grp < T) ep0(grp);
+    }
+    for (int k = grp; k < T; k += NG) {
+      const int tile = tile_of(k);
+      const uint32_t par = (uint32_t)(k / NG) & 1;
+      ep1(k);
+      if constexpr (!full) continue;
       // ---- epilogue 2: +bias, PReLU, + residual, PReLU, 16-bit -> y tile (in place over x; narrow: own buffer)
       const int xb = k % NX;
       uint8_t* yt = smem + S::OFF_X + (NARROW ? grp : xb) * S::XBUF;
@@ -473,6 +554,10 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           }
         }
       }
+      // ---- pulled forward: the epilogue that feeds the group's next tile (see above)
+      if constexpr (ASYM) {
+        if (k + NG < T) ep0(k + NG);
+      }
       // ---- epilogue 3: the next block's projection: +bias, PReLU, 16-bit -> e1' (global)
       if (p.has_next) {
         mbar_wait(bar(S::D3_FULL + grp), par);
@@ -512,7 +597,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     if constexpr (EPW == 1) {
       run(std::integral_constant<int, 0>{});
     } else {
-      if (((warp - 4) >> 2) % EPW == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
+      if (((warp - S::SERVICE) >> 2) % EPW == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
     }
   }
   // ---- teardown
@@ -665,10 +750,10 @@ static bool build_t(UmmaPack& out, const float* conv_w, int ntaps, const float* 
   return true;
 }
 
-template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false, int EPW = 1>
+template <int C, int CI, int CN, int CRES, int NG, int MINB, bool CONV = false, int EPW = 1, bool ASYM = false>
 static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,
                               int W, const Taps& taps, int ntaps, int conv_only, int has_next, int num_sms, cudaStream_t s) {
-  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV, EPW>;
+  using S = UmmaSmem<C, CI, CN, CRES, NG, MINB, CONV, EPW, ASYM>;
   CUtensorMap me1, mx, my;
   // row-slab mode: a plain 3x3 conv (dilation 1, taps in row-major order) whose 128-pixel tile is one image row
   static const bool no_rowslab = getenv("BC_NO_ROWSLAB") != nullptr, no_vslab = getenv("BC_NO_VSLAB") != nullptr,
@@ -689,7 +774,12 @@ static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* 
   // vertical-slab mode: a 5x1 conv (taps dy = -2..2, dx = 0) whose tile is two full-width rows of 64 pixels
   bool vslab = CI == 32 && S::NRING == 9 && ntaps == 5 && W == 64 && !no_vslab;
   for (int t = 0; vslab && t < 5; ++t) vslab = taps.dy[t] == t - 2 && taps.dx[t] == 0;
-  if (pairslab ? !make_map_pair(&me1, e1, n, H, W, CI, 64 + 2 * pair_halo)
+  if (ASYM) {        // fused asymmetric block: `taps` are the 5x1 taps (vertical slab from the ring); the 1x5 half runs on-chip
+    if (!vslab || W != 64 || H % 2 != 0) return cudaErrorInvalidValue;
+    pairslab = true; pair_step = 1; pair_halo = 2;      // lane order of D1 and of the later epilogues
+  }
+  if (ASYM ? !make_map_box(&me1, e1, n, H, W, CI, 64, 6)
+      : pairslab ? !make_map_pair(&me1, e1, n, H, W, CI, 64 + 2 * pair_halo)
       : rowslab ? !make_map_box(&me1, e1, n, H, W, CI, 130, 1)
       : vslab ? !make_map_box(&me1, e1, n, H, W, CI, 64, 6) : !make_map_e1(&me1, e1, n, H, W, CI))
     return cudaErrorInvalidValue;
@@ -730,9 +820,9 @@ static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW>, me1, mx, my, p);
+    return cudaLaunchKernelEx(&cfg, k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW, ASYM>, me1, mx, my, p);
   }
-  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
+  k_umma_bottleneck<C, CI, CN, CRES, NG, MINB, CONV, EPW, ASYM><<<grid, S::THREADS, smem, s>>>(me1, mx, my, p);
   return cudaGetLastError();
 }
 
@@ -762,6 +852,9 @@ cudaError_t Umma<act_t>::prepare_bottleneck() {
                              cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaSmem<C_, CI_, CN_, CR_, NG_, MB_, CV_, EP_>::TOTAL + 1024);
   BC_UMMA_CONFIGS(BC_SET)
 #undef BC_SET
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_umma_bottleneck<128, 32, 32, 128, 2, 1, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             UmmaSmem<128, 32, 32, 128, 2, 1, false, 1, true>::TOTAL + 1024);
   return e;
 }
 
@@ -779,6 +872,45 @@ bool Umma<act_t>::build(UmmaPack& out, int C, int CI, int CN, int CRES, const fl
     ok = build_t<128, 16, 32>(out, conv_w, ntaps, conv_b, conv_a, exp_w, exp_b, exp_a, alpha_out, next_w, next_b, next_a);
   out.CRES = CRES;
   return ok;
+}
+
+// Fused asymmetric block (128 channels): W2 area = 5 taps of the 5x1 conv then 5 taps of the 1x5 conv; the fp32 block
+// ends with the 5x1 conv's bias / slope.
+bool Umma<act_t>::build_asym(UmmaPack& out, const float* c0_w, const float* c0_b, const float* c0_a, const float* c1_w,
+                             const float* c1_b, const float* c1_a, const float* exp_w, const float* exp_b, const float* exp_a,
+                             const float* alpha_out, const float* next_w, const float* next_b, const float* next_a) {
+  constexpr int C = 128, CI = 32, CN = 32;
+  using Wt = UmmaWeights<C, CI, CN, 10>;
+  std::vector<uint8_t> img(Wt::W_BYTES, 0);
+  std::vector<float> w0(c0_w, c0_w + (size_t)5 * CI * CI), w1(c1_w, c1_w + (size_t)5 * CI * CI);
+  for (int t = 0; t < 5; ++t) {
+    pack_rows(img.data() + Wt::OFF_W2 + t * Wt::W2_TAP, CI, Wt::RB, w0, CI, CI, t, 0);
+    pack_rows(img.data() + Wt::OFF_W2 + (5 + t) * Wt::W2_TAP, CI, Wt::RB, w1, CI, CI, t, 0);
+  }
+  std::vector<float> ew(exp_w, exp_w + (size_t)CI * C);
+  pack_rows(img.data() + Wt::OFF_W3, C, Wt::RB, ew, CI, C, 0, 0);
+  if (next_w) {
+    std::vector<float> nw(next_w, next_w + (size_t)C * CN);
+    for (int sidx = 0; sidx < Wt::NSUB; ++sidx) pack_rows(img.data() + Wt::OFF_W1 + sidx * Wt::W1_SUB, CN, 128, nw, C, CN, 0, sidx * 64);
+  }
+  std::vector<float> f(Wt::NF, 0.f);
+  float* b2 = f.data(); float* a2 = b2 + CI; float* b3 = a2 + CI; float* a3 = b3 + C; float* ao = a3 + C;
+  float* b1n = ao + C; float* a1n = b1n + CN; float* b0 = a1n + CN; float* a0 = b0 + CI;
+  for (int j = 0; j < CI; ++j) { b2[j] = c1_b[j]; a2[j] = c1_a[j]; b0[j] = c0_b[j]; a0[j] = c0_a[j]; }
+  for (int j = 0; j < C; ++j) { b3[j] = exp_b[j]; a3[j] = exp_a[j]; ao[j] = alpha_out[j]; }
+  if (next_w) for (int j = 0; j < CN; ++j) { b1n[j] = next_b[j]; a1n[j] = next_a[j]; }
+  if (cudaMalloc(&out.wblob, Wt::W_BYTES) != cudaSuccess) return false;
+  cudaMemcpy(out.wblob, img.data(), Wt::W_BYTES, cudaMemcpyHostToDevice);
+  out.hf = f;
+  out.C = C; out.CI = CI; out.CN = CN; out.CRES = C; out.ntaps = 5; out.has_exp = true; out.has_next = next_w != nullptr;
+  return true;
+}
+
+// e1: the block's projection; taps5x1: (dy = -2..2, dx = 0)
+cudaError_t Umma<act_t>::launch_asym(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,
+                                     int W, const Taps& taps5x1, int has_next, int num_sms, cudaStream_t s) {
+  if (pk.C != 128 || pk.CI != 32 || W != 64) return cudaErrorInvalidValue;
+  return launch_one<128, 32, 32, 128, 2, 1, false, 1, true>(pk, e1, x, y, out_small, n, H, W, taps5x1, 5, 0, has_next, num_sms, s);
 }
 
 cudaError_t Umma<act_t>::launch(const UmmaPack& pk, const act_t* e1, const act_t* x, act_t* y, act_t* out_small, int n, int H,

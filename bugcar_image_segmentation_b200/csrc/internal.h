@@ -41,6 +41,7 @@ struct Bottleneck {
   ConvP c1, c2, c2b, c3, cm; // proj / mid / mid-second (asym) / expand / main (up)
   float* alpha_out = nullptr;
   std::vector<float> s5;     // Stage5Params image (host) when the block is the 16-channel regular bottleneck
+  UmmaPack um_f;             // asymmetric bottleneck fused into one kernel (5x1 + 1x5 + expansion + residual + next projection)
   UmmaPack um_a, um_b;       // um_b: second half (1x5 + expansion) of an asymmetric bottleneck; first half (pool + 2x2 conv) of a down-sampling one
 };
 

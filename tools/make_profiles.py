@@ -20,6 +20,7 @@ RULES = [   # (regex on the demangled kernel name, bench.py kernel label)
     (r"k_umma_bottleneck<128, 16, 32, 64", "umma_down128"),
     (r"k_umma_bottleneck<64, 16, 16, 64", "umma_bottleneck64"),
     (r"k_umma_bottleneck<128, 32, 32, 128, 2, 2, 1", "umma_conv5x1"),
+    (r"k_umma_bottleneck<128, 32, 32, 128, 2, 1, 0, 1, 1>", "umma_asym_fused"),
     (r"k_umma_bottleneck<128, 32, 32, 128", "umma_bottleneck128"),      # regular / dilated and the 1x5 halves
     (r"k_umma_up<128", "umma_up4"),
     (r"k_umma_up<64", "umma_up5"),
