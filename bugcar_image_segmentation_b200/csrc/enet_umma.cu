@@ -100,6 +100,7 @@ struct UmmaSmem {
   // residual buffer (each group then owns one x / y buffer) and to let D3 (next projection) reuse D1's TMEM
   // columns (D1 is dead once epilogue 1 has read it): 3 x (32 + 128) = 480 of 512 columns
   static constexpr bool ALIAS13 = !CONV && !NARROW && NG >= 3 && C == 128;
+  // (a second spare buffer paid for with the tap ring -- four x buffers, one tile of taps -- measured 68.5 vs 65.6 us)
   static constexpr int NX = ALIAS13 ? NG : NG + 1;  // residual tile ring (one tile of prefetch)
   static constexpr int NY = CONV ? 0 : NARROW ? NG : NX;   // C-wide tiles: x/y in place, or one y per group
   static constexpr int RES_RB = CRES * 2 >= 128 ? 128 : CRES * 2;   // row bytes / swizzle of a narrow residual tile
@@ -482,8 +483,8 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
     // fused asymmetric block the extra stage is hidden by software pipelining: ep0(k + NG) runs right after ep2(k),
     // while tile k's projection MMAs run, and the next tile's 1x5 MMAs run under ep3(k) (82 -> 77 us per launch; the
     // slab is free: the MMAs that read it finished before the D1 / D2 barriers this group has passed).  Pulling ep1
-    // forward the same way in the ordinary blocks was measured SLOWER (65 -> 69 us: the issuer warps serve the groups
-    // in tile order, and the later ep3 delays the residual buffer's refill), so they keep program order.
+    // forward the same way in the ordinary blocks was measured SLOWER (65 -> 69 us, also when done only if the
+    // accumulator is already there: the later ep3 delays the residual buffer's refill), so they keep program order.
     if constexpr (ASYM) {
       if (grp < T) ep0(grp);
     }
