@@ -23,6 +23,12 @@ static constexpr int S5_HW = S5_TW + 2, S5_HH = S5_TH + 2;      // with halo
 // their indices are compile-time constants, so each one is a constant-bank operand of its FFMA
 // (the kernel was shared-memory-pipe bound, 93 % l1tex, when it fetched them with LDS).
 
+// Packed fp32 FMA (FFMA2, sm_100): two independent round-to-nearest FMAs per instruction -- bit-identical to the
+// scalar form, half the issue slots.  The kernel is issue-bound (95 %), and 43 % of its instructions were FFMAs.
+__device__ __forceinline__ float2 fma2(float s, const float* w2, float2 acc) {      // acc + s * (w2[0], w2[1])
+  return __ffma2_rn(make_float2(s, s), *reinterpret_cast<const float2*>(w2), acc);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ Stage5Params p, int H, int W,
@@ -44,11 +50,13 @@ k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, const __grid_con
     if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
       float v[16];
       ld_ch<16>(xf + ((size_t)gy * W + gx) * 16, v);
-      float a[4] = {p.b1[0], p.b1[1], p.b1[2], p.b1[3]};
+      float2 a01 = make_float2(p.b1[0], p.b1[1]), a23 = make_float2(p.b1[2], p.b1[3]);
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = fmaf(v[k], p.w1[4 * k + j], a[j]);
+      for (int k = 0; k < 16; ++k) {
+        a01 = fma2(v[k], &p.w1[4 * k], a01);
+        a23 = fma2(v[k], &p.w1[4 * k + 2], a23);
+      }
+      const float a[4] = {a01.x, a01.y, a23.x, a23.y};
       e = make_float4(rnd<T>(prelu(a[0], p.a1[0])), rnd<T>(prelu(a[1], p.a1[1])), rnd<T>(prelu(a[2], p.a1[2])),
                       rnd<T>(prelu(a[3], p.a1[3])));
     }
@@ -62,27 +70,32 @@ k_stage5_bottleneck(const T* __restrict__ x, T* __restrict__ y, const __grid_con
     const int ly = (tid >> 5) + 4 * r, lx = tid & 31;          // a warp covers one tile row: coalesced
     const int gy = y0 + ly, gx = x0 + lx;
     if (gy >= H || gx >= W) continue;
-    float a[4] = {p.b2[0], p.b2[1], p.b2[2], p.b2[3]};
+    float2 a01 = make_float2(p.b2[0], p.b2[1]), a23 = make_float2(p.b2[2], p.b2[3]);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const float4 e = se1[(ly + t / 3) * S5_HW + lx + t % 3];
       const float ev[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = fmaf(ev[k], p.w2[(t * 4 + k) * 4 + j], a[j]);
+      for (int k = 0; k < 4; ++k) {
+        a01 = fma2(ev[k], &p.w2[(t * 4 + k) * 4], a01);
+        a23 = fma2(ev[k], &p.w2[(t * 4 + k) * 4 + 2], a23);
+      }
     }
+    const float a[4] = {a01.x, a01.y, a23.x, a23.y};
     float e2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) e2[j] = rnd<T>(prelu(a[j], p.a2[j]));
     float o[16], xr[16];
     ld_ch<16>(xf + ((size_t)gy * W + gx) * 16, xr);
+    float2 o2[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = p.b3[j];
+    for (int j = 0; j < 8; ++j) o2[j] = make_float2(p.b3[2 * j], p.b3[2 * j + 1]);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) o[j] = fmaf(e2[k], p.w3[k * 16 + j], o[j]);
+      for (int j = 0; j < 8; ++j) o2[j] = fma2(e2[k], &p.w3[k * 16 + 2 * j], o2[j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[2 * j] = o2[j].x; o[2 * j + 1] = o2[j].y; }
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = prelu(prelu(o[j], p.a3[j]) + xr[j], p.aout[j]);
     st_ch<16>(yf + ((size_t)gy * W + gx) * 16, o);
