@@ -299,9 +299,14 @@ def main():
         # i-1's kernels; returns when step i-1's grids are on the host (one step in flight).  N > 1: the same two
         # calls per rank -- K9 stores into rank 0's gather buffer, flags in peer-mapped memory order the ranks,
         # rank 0's context copies each complete step to ITS host buffer (sharding.StreamingGather)
+        t0 = time.perf_counter()
         model.ctx.pipeline_host_submit(pinned[i % N_INPUT_SETS], 256, 512, B, pipe.lut, *GRID, 0, 0,
                                        pinned_out2[i & 1] if rank == 0 else None, stream.cuda_stream)
+        t1 = time.perf_counter()
         model.ctx.pipeline_host_wait(1)
+        trace.append((t1 - t0, time.perf_counter() - t1))
+
+    trace = []      # per step: host seconds inside submit / inside wait (BC_E2E_TRACE=1 prints a per-rank summary)
 
     def timed(fn, steps, finish=None):
         barrier()
@@ -344,6 +349,10 @@ def main():
             step_e2e(i)
         model.ctx.pipeline_host_wait(0)
     ms_e2e = timed(step_e2e, args.steps, finish=lambda: model.ctx.pipeline_host_wait(0))
+    if os.environ.get("BC_E2E_TRACE"):
+        tr = np.array(trace[-args.steps:])
+        print(f"[rank {rank}] e2e host time per step: submit {tr[:, 0].mean() * 1e3:.3f} ms (max {tr[:, 0].max() * 1e3:.3f}), "
+              f"wait {tr[:, 1].mean() * 1e3:.3f} ms (max {tr[:, 1].max() * 1e3:.3f})", file=sys.stderr, flush=True)
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     # the ceiling the end-to-end number lives under: every rank's bare pinned-host -> device copies of the same
