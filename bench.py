@@ -228,9 +228,13 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     from bugcar_image_segmentation_b200 import runtime
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # which GPU this rank takes: the local rank, unless the node has more GPUs than the job has ranks -- then the ranks
+    # are spread over the node's two host domains (runtime.device_for_rank: 4 ranks on GPUs 0-3 share 116 GB/s of
+    # H2D bandwidth, on GPUs 0, 4, 1, 5 they get 218 GB/s)
+    local = runtime.device_for_rank(local_rank, world)
+    torch.cuda.set_device(local)
     host_bind = runtime.bind_host_to_gpu(local)     # before any pinned allocation: staging buffers local to the GPU's NUMA node
     # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there
     # when NCCL_DEBUG is set) go to stderr until the result is printed
@@ -582,7 +586,8 @@ def main():
                        parallelism=f"frame-sharded dp{world}" + ("" if world == 1 else ", grids gathered to rank 0 (NCCL gather)"
                                                                  if peer is None else ", grids stored by K9 into rank 0's "
                                                                  "peer-mapped buffer (NVLink), one barrier per step"),
-                       chunk=args.chunk, tensor_cores=not args.no_tc),
+                       chunk=args.chunk, tensor_cores=not args.no_tc,
+                       devices=[runtime.device_for_rank(r, world) for r in range(world)]),
             "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": B * 393216, "d2h_bytes_per_step": (world if world > 1 else 1) * B * Hc * Wc,
                     "api": "bc_pipeline_host_submit / bc_pipeline_host_wait on every rank" +

@@ -80,3 +80,21 @@ def bind_host_to_gpu(device):
     except (OSError, ValueError):
         pass
     return info
+
+
+def device_for_rank(local_rank, world, n_visible=None):
+    """Which GPU a rank of an N-rank job on one node should take when the node has MORE GPUs than ranks.
+    On the 8 x B200 boxes of this pool GPUs 0-3 and GPUs 4-7 hang off two host domains that each deliver ~ 116 GB/s
+    of pinned-host -> device copies (one GPU alone: 55 GB/s; measured by bench.py's h2d ceiling): four ranks on GPUs
+    0-3 share one domain (116 GB/s), four ranks on GPUs 0, 4, 1, 5 get 218 GB/s.  The VM exposes neither NUMA nor
+    PCIe locality, so the rule is positional: ranks alternate between the two halves of the visible devices.
+    BUGCAR_DEVICE_MAP="0,4,1,5" overrides, BUGCAR_DEVICE_MAP="identity" switches the spreading off."""
+    import torch
+    n = torch.cuda.device_count() if n_visible is None else n_visible
+    env = os.environ.get("BUGCAR_DEVICE_MAP", "")
+    if env and env != "identity":
+        m = [int(v) for v in env.split(",")]
+        return m[local_rank % len(m)]
+    if env == "identity" or world >= n or n < 2 or n % 2:
+        return local_rank
+    return (local_rank // 2) + (local_rank % 2) * (n // 2)

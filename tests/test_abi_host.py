@@ -189,3 +189,19 @@ def test_laser_tables_match_oracle():
             assert binary or (pw, ph) == laser_oracle.polar_dsize(radius)
             assert np.array_equal(fwd, laser_oracle.forward_map(pw, ph, centre[0], centre[1], radius, wc, hc))
             assert np.array_equal(inv, laser_oracle.inverse_map(wc, hc, centre[0], centre[1], radius, pw, ph))
+
+
+def test_rank_placement_spreads_over_both_host_domains(monkeypatch):
+    """runtime.device_for_rank: identity when the job fills the node (or the node shows exactly N GPUs), alternate halves
+    otherwise; BUGCAR_DEVICE_MAP overrides"""
+    from bugcar_image_segmentation_b200 import runtime
+    monkeypatch.delenv("BUGCAR_DEVICE_MAP", raising=False)
+    assert [runtime.device_for_rank(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [runtime.device_for_rank(r, 4, 4) for r in range(4)] == [0, 1, 2, 3]
+    assert [runtime.device_for_rank(r, 4, 8) for r in range(4)] == [0, 4, 1, 5]
+    assert [runtime.device_for_rank(r, 2, 8) for r in range(2)] == [0, 4]
+    assert runtime.device_for_rank(0, 1, 8) == 0 and runtime.device_for_rank(0, 1, 1) == 0
+    monkeypatch.setenv("BUGCAR_DEVICE_MAP", "identity")
+    assert [runtime.device_for_rank(r, 4, 8) for r in range(4)] == [0, 1, 2, 3]
+    monkeypatch.setenv("BUGCAR_DEVICE_MAP", "3,2,1,0")
+    assert [runtime.device_for_rank(r, 4, 8) for r in range(4)] == [3, 2, 1, 0]
