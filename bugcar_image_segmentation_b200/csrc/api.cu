@@ -140,7 +140,7 @@ struct bc_ctx {
   // ---- resize tables, keyed by source size
   std::map<std::pair<int, int>, ResizeTab> resize_tabs;
   // ---- K9 coordinate tables, keyed by the geometry (cleared by bc_set_bev)
-  std::vector<std::pair<BevGeom, uint4*>> occ_tables;
+  std::vector<std::pair<BevGeom, uint2*>> occ_tables;
 
   // ---- contour_noise_removal (image_processing_utils.py:4-44)
   void* cn_scratch = nullptr;
@@ -1096,8 +1096,8 @@ int make_geom(bc_ctx* c, double w_m, double h_m, double cell_m, int binary, int 
   for (auto& kv : c->occ_tables)
     if (memcmp(&kv.first, &key, sizeof key) == 0) { g.table = kv.second; return BC_OK; }
   CU(cudaSetDevice(c->device));
-  uint4* d = nullptr;
-  CU(cudaMalloc(&d, (size_t)25 * Hc * Wc * sizeof(uint4)));
+  uint2* d = nullptr;
+  CU(cudaMalloc(&d, occ_table_bytes(Hc * Wc)));
   launch_occ_table(key, d, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { cudaFree(d); return fail(c, BC_ERR_CUDA, std::string("occupancy table: ") + cudaGetErrorString(e)); }
@@ -1381,7 +1381,8 @@ int bc_set_host_overlap(bc_ctx* c, int enable) {
 int bc_set_bev(bc_ctx* c, const double h_M[9], int in_rows, int in_cols, int warp_w, int warp_h, double cm_per_px) {
   if (!c) return BC_ERR_ARG;
   if (!h_M) return fail(c, BC_ERR_ARG, "null matrix");
-  if (in_rows < 1 || in_cols < 1 || in_rows > 32767 || in_cols > 32767) return fail(c, BC_ERR_ARG, "label-map size out of range");
+  if (in_rows < 2 || in_cols < 2 || in_rows > 32767 || in_cols > 32767)          // K9 samples fixed 2 x 2 blocks of label pixels
+    return fail(c, BC_ERR_ARG, "label-map size out of range (2..32767 per side)");
   if (warp_w < 1 || warp_h < 1 || warp_w > 32767 || warp_h > 32767) return fail(c, BC_ERR_ARG, "warped size out of range");
   if (!(cm_per_px > 0.0)) return fail(c, BC_ERR_ARG, "cm_per_px must be positive");
   CU(cudaSetDevice(c->device));

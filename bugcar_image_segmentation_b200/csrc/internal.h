@@ -70,7 +70,7 @@ struct BevGeom {            // kernel parameter block for K9 (passed by value)
   int binary, ros_layout;
   int raw_template;         // 1: write the resized template value (0..3) instead of the int8 map (laserscan branch)
   double ifx, ify;          // nearest-resize source step (cv::resize INTER_NEAREST, fp64)
-  const uint4* table;       // device table of k_occ_table for this geometry ([25][Hc*Wc]); host-side cache key has it null
+  const uint2* table;       // device table of k_occ_table for this geometry (uint2 [25][Hc*Wc] + uint32 [Hc*Wc]); host-side cache key has it null
 };
 
 // ------------------------------------------------------------------ launchers (enet_simt.cu)
@@ -129,7 +129,8 @@ void launch_preprocess(const uint8_t* bgr256, int B, void* out, int out_f64, con
                        cudaStream_t s);
 void launch_argmax_lut(const float* logits, int B, int C, int H, int W, const Lut256& lut,
                        uint8_t* labels, cudaStream_t s);
-void launch_occ_table(const BevGeom& g, uint4* table, cudaStream_t s);     // [25][Hc*Wc] entries, once per geometry
+size_t occ_table_bytes(int cells);
+void launch_occ_table(const BevGeom& g, uint2* table, cudaStream_t s);     // occ_table_bytes(Hc*Wc) bytes, once per geometry
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s);   // needs g.table
 cudaError_t prepare_occgrid();            // dynamic shared-memory opt-in of K9 on the current device
 

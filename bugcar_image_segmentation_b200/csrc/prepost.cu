@@ -152,8 +152,23 @@ __device__ __forceinline__ void warp_coords(const BevGeom& g, int x, int y, int&
   Y = __double2int_rn(fY);
 }
 
+// Table entry (8 bytes) of one template pixel: its bilinear footprint in the label map as a fixed 2 x 2 block of
+// label pixels (rows r, r + 1, columns b, b + 1, always inside the image) and the separable weights of those
+// four pixels -- zero for taps outside the image (cv::remap BORDER_CONSTANT 0), moved to the other column / row
+// where the clamped block starts one pixel off the footprint (first and last column / row):
+//   .x = r * cols + b
+//   .y = wx0 | wx1 << 8 | wy0 << 16 | wy1 << 24      (weights 0..32)
+// The 25 entries of a cell are followed by one word per cell whose bit `pos` says that position lies in the
+// template (layout: uint2 [25][cells], uint32 [cells]).
+__device__ __forceinline__ void occ_axis(int s, int a, int n, int& base, unsigned& w0, unsigned& w1) {
+  base = 0; w0 = 0; w1 = 0;
+  if (s >= 0 && s + 1 < n) { base = s; w0 = 32 - a; w1 = a; }
+  else if (s == -1) { w0 = a; }                               // only pixel 0 (the footprint's second tap) is inside
+  else if (s == n - 1) { base = n - 2; w1 = 32 - a; }         // only pixel n-1 (the footprint's first tap) is inside
+}
+
 __global__ void __launch_bounds__(128)
-k_occ_table(const BevGeom g, uint4* __restrict__ table) {
+k_occ_table(const BevGeom g, uint2* __restrict__ table, unsigned* __restrict__ inside) {
   const int cells = g.Hc * g.Wc;
   int cell = blockIdx.x * blockDim.x + threadIdx.x;
   int pos = blockIdx.y;
@@ -163,9 +178,9 @@ k_occ_table(const BevGeom g, uint4* __restrict__ table) {
   int tx = min((int)floor(__dmul_rn((double)cx, g.ifx)), g.occ_w_px - 1);
   int ty = min((int)floor(__dmul_rn((double)cy, g.ify)), g.occ_h_px - 1);
   int x = tx - 2 + pos % 5, y = ty - 2 + pos / 5;
-  uint4 e = make_uint4(0u, 0u, 0u, 0u);
+  uint2 e = make_uint2(0u, 0u);
   if (x >= 0 && x < g.occ_w_px && y >= 0 && y < g.occ_h_px) {
-    e.w = 4;
+    atomicOr(&inside[cell], 1u << pos);
     // crop of the warped image pasted into a zero template (bev.py:183-195)
     int px = x - g.gl, py = y - g.gt;
     if (px >= 0 && py >= 0 && px < g.crop_w && py < g.crop_h) {
@@ -173,88 +188,91 @@ k_occ_table(const BevGeom g, uint4* __restrict__ table) {
       warp_coords(g, px + g.wl, py + g.wt, X, Y);
       const int sx = min(max(X >> 5, -32768), 32767);   // saturate_cast<short>
       const int sy = min(max(Y >> 5, -32768), 32767);
-      const int ax = X & 31, ay = Y & 31;
-      const int rows = g.in_rows, cols = g.in_cols;
-      const bool vx0 = sx >= 0 && sx < cols, vx1 = sx + 1 >= 0 && sx + 1 < cols;
-      const bool vy0 = sy >= 0 && sy < rows, vy1 = sy + 1 >= 0 && sy + 1 < rows;
-      const int x0 = min(max(sx, 0), cols - 1), x1 = min(max(sx + 1, 0), cols - 1);
-      const int y0 = min(max(sy, 0), rows - 1), y1 = min(max(sy + 1, 0), rows - 1);
-      const unsigned wx0 = vx0 ? 32 - ax : 0, wx1 = vx1 ? ax : 0, wy0 = vy0 ? 32 - ay : 0, wy1 = vy1 ? ay : 0;
-      e.x = (unsigned)(y0 * cols + x0);
-      e.y = (wy0 * wx0) | ((wy0 * wx1) << 16);
-      e.z = (wy1 * wx0) | ((wy1 * wx1) << 16);
-      e.w |= (unsigned)(x1 - x0) | ((unsigned)(y1 - y0) << 1);
+      int bx, by;
+      unsigned wx0, wx1, wy0, wy1;
+      occ_axis(sx, X & 31, g.in_cols, bx, wx0, wx1);
+      occ_axis(sy, Y & 31, g.in_rows, by, wy0, wy1);
+      e.x = (unsigned)(by * g.in_cols + bx);
+      e.y = wx0 | (wx1 << 8) | (wy0 << 16) | (wy1 << 24);
     }
   }
   table[(size_t)pos * cells + cell] = e;
 }
 
-void launch_occ_table(const BevGeom& g, uint4* table, cudaStream_t s) {
-  dim3 grid((g.Hc * g.Wc + 127) / 128, 25);
-  k_occ_table<<<grid, 128, 0, s>>>(g, table);
+size_t occ_table_bytes(int cells) { return (size_t)cells * (25 * sizeof(uint2) + sizeof(unsigned)); }
+
+void launch_occ_table(const BevGeom& g, uint2* table, cudaStream_t s) {
+  const int cells = g.Hc * g.Wc;
+  unsigned* inside = reinterpret_cast<unsigned*>(table + (size_t)25 * cells);
+  cudaMemsetAsync(inside, 0, (size_t)cells * sizeof(unsigned), s);
+  dim3 grid((cells + 127) / 128, 25);
+  k_occ_table<<<grid, 128, 0, s>>>(g, table, inside);
 }
 
-// (labels + 1) blended at the table entry's footprint: (sum p * w + 512) >> 10;
-// np.add(segmap, 1) wraps in uint8 (bev.py:177)
-__device__ __forceinline__ int occ_sample(const uint8_t* __restrict__ lab, uint4 e, int cols) {
-  const uint8_t* p0 = lab + e.x;
-  const uint8_t* p1 = p0 + ((e.w & 2) ? cols : 0);
-  const unsigned dx = e.w & 1;
-  // the four taps as bytes of one word, +1 per byte with uint8 wrap-around, then two 2-way dot products of
-  // 16-bit weights x bytes (dp2a): same integers as the scalar form, a third fewer instructions
-  const unsigned top = (unsigned)p0[0] | ((unsigned)p0[dx] << 8), bot = (unsigned)p1[0] | ((unsigned)p1[dx] << 8);
-  const unsigned px = __vadd4(top | (bot << 16), 0x01010101u);
-  unsigned acc = __dp2a_lo(e.y, px, 512u);        // w00 * byte 0 + w01 * byte 1
-  acc = __dp2a_hi(e.z, px, acc);                  // w10 * byte 2 + w11 * byte 3
-  return (int)(acc >> 10);
+// (labels + 1) blended at the table entry's footprint: (sum p * wy * wx + 512) >> 10, evaluated as
+// wy0 * (wx0 p00 + wx1 p01) + wy1 * (wx0 p10 + wx1 p11) -- the same integer -- in three dp2a;
+// np.add(segmap, 1) wraps in uint8 (bev.py:177).  `nb` = frame index * rows * cols (32 bits: launch_occgrid
+// splits batches whose label maps exceed 4 GB).
+__device__ __forceinline__ unsigned occ_sample(const uint8_t* __restrict__ labels, unsigned nb, uint2 e, int cols) {
+  const uint8_t* p0 = labels + (nb + e.x);
+  const uint8_t* p1 = p0 + cols;
+  // a row's two pixels as the 16-bit halves of one word, + 1 each with uint8 wrap-around
+  const unsigned top = (((unsigned)p0[1] << 16 | (unsigned)p0[0]) + 0x00010001u) & 0x00ff00ffu;
+  const unsigned bot = (((unsigned)p1[1] << 16 | (unsigned)p1[0]) + 0x00010001u) & 0x00ff00ffu;
+  const unsigned t = __dp2a_lo(top, e.y, 0u);          // p00 * wx0 + p01 * wx1   (<= 255 * 32)
+  const unsigned b = __dp2a_lo(bot, e.y, 0u);
+  return __dp2a_hi(b << 16 | t, e.y, 512u) >> 10;      // t * wy0 + b * wy1 + 512
 }
 
-__device__ __forceinline__ bool is_occ(int v, int binary) {
-  return binary ? (v == 1) : (v == 1 || v == 3);   // bev.py:128 / bev.py:196
+__device__ __forceinline__ bool is_occ(unsigned v, int binary) {
+  return binary ? (v == 1u) : ((v | 2u) == 3u);     // 1, or 1 / 3: bev.py:128 / bev.py:196
 }
 
-// One thread per grid cell, `fpb` frames per block (the block's slice of the table is staged in
-// shared memory once and reused for every frame).  Blocks stay small (8 frames): the cost of a cell
-// depends on the scene (occupied cells sample up to 25 template pixels, free ones a single one), so
-// many short blocks balance themselves over the SMs; one resident wave of 37-frame blocks measured
-// 129 us against 105 us (the slowest block sets the time).  The cell takes template pixel
-// (ty, tx) (nearest resize); if that pixel is "occupied" the 3x3 opening decides whether it
-// is a speck:
+// One thread per grid cell, `fpb` frames per block.  The cell takes template pixel (ty, tx) (nearest
+// resize); if that pixel is "occupied" the 3x3 opening decides whether it is a speck:
 //   opened(p) = OR_{q in N3(p)} AND_{r in N3(q)} occ(r)   (erode ignores pixels outside
 //   the template, dilate treats them as 0 -- OpenCV default border values)
 // evaluated lazily: q = p needs only the inner 3x3 ring; the outer ring of the 5x5 block is
 // sampled only when that fails (the interior of an occupied region never gets there).
+//
+// The kernel is a chain of dependent gathers (centre -> inner ring -> outer ring), so what it needs is
+// loads in flight: the nine inner table entries of the cell live in registers for all frames of the block
+// (no shared memory: 8 blocks of 128 threads per SM), the centre samples of OCC_CH frames are issued
+// together before any of them is consumed, and the rarely needed outer-ring entries come from the table in
+// global memory (L2 resident, 2 MB).  Blocks stay small: the cost of a cell depends on the scene (occupied
+// cells sample up to 25 template pixels, free ones a single one), so many short blocks balance themselves
+// over the SMs; one resident wave of 37-frame blocks measured 129 us against 105 us.
 static constexpr unsigned OCC_INNER = (7u << 6) | (7u << 11) | (7u << 16);     // 3x3 block around bit 12
+static constexpr int OCC_CH = 4;             // frames whose centre samples are in flight together
+static constexpr int OCC_MINB = 8;           // resident blocks per SM the register budget is set for
 
 // outer ring of the 5x5 block, k = 0..15 -> bit position
 __device__ __forceinline__ int occ_outer_pos(int k) {
   return k < 5 ? k : (k < 11 ? 5 * (((k - 5) >> 1) + 1) + ((k - 5) & 1) * 4 : k + 9);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, OCC_MINB)
 k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int fpb, int8_t* __restrict__ grids) {
-  extern __shared__ uint4 tab[];                  // [25][128]
-  const uint4* __restrict__ table = g.table;
+  const uint2* __restrict__ table = g.table;
   const int cells = g.Hc * g.Wc;
   const int cell = blockIdx.x * 128 + threadIdx.x;
   const bool live = cell < cells;
   const int lane = threadIdx.x & 31, half = lane >> 4, k16 = lane & 15;
   const unsigned half_mask = half ? 0xffff0000u : 0x0000ffffu;
-  unsigned inside = 0;
+  uint2 ein[9];                    // inner 3x3 block, [j * 3 + i] <-> position (1 + j) * 5 + (1 + i)
 #pragma unroll
-  for (int pos = 0; pos < 25; ++pos) {
-    uint4 e = live ? table[(size_t)pos * cells + cell] : make_uint4(0u, 0u, 0u, 0u);
-    tab[pos * 128 + threadIdx.x] = e;
-    if (e.w & 4u) inside |= 1u << pos;
-  }
-  __syncwarp();                    // a warp reads back only its own 32 columns: no block barrier needed
+  for (int k = 0; k < 9; ++k)
+    ein[k] = live ? table[(size_t)((1 + k / 3) * 5 + 1 + k % 3) * cells + cell] : make_uint2(0u, 0u);
+  const unsigned inside = live ? reinterpret_cast<const unsigned*>(table + (size_t)25 * cells)[cell] : 0u;
   const int cx = cell % g.Wc, cy = cell / g.Wc;
   const size_t o = g.ros_layout ? (size_t)(g.Wc - 1 - cx) * g.Hc + (g.Hc - 1 - cy)   // occgrid_to_ros.py:18-21
                                 : (size_t)cell;
-  const int rows = g.in_rows, cols = g.in_cols;
+  const int cols = g.in_cols;
+  const unsigned frame = (unsigned)g.in_rows * (unsigned)cols;
   const int n1 = min(B, (int)(blockIdx.y + 1) * fpb);
   // what this lane does when it helps with another lane's outer ring / opening test
   const int my_outer = occ_outer_pos(k16);
+  const uint2* __restrict__ my_outer_row = table + (size_t)my_outer * cells + (cell - lane);
   unsigned my_q = 0, my_nb = 0;                    // lanes 0..8 of each half: one erosion centre q each
   if (k16 < 9) {
     const int qj = 1 + k16 / 3, qi = 1 + k16 % 3;
@@ -262,72 +280,78 @@ k_occgrid(const uint8_t* __restrict__ labels, const BevGeom g, int B, int fpb, i
     for (int rj = -1; rj <= 1; ++rj)
       for (int ri = -1; ri <= 1; ++ri) my_nb |= 1u << ((qj + rj) * 5 + (qi + ri));
   }
-  for (int n = blockIdx.y * fpb; n < n1; ++n) {
-    const uint8_t* lab = labels + (size_t)n * rows * cols;
-    int v = occ_sample(lab, tab[12 * 128 + threadIdx.x], cols);
-    const bool occupied = live && is_occ(v, g.binary);
-    unsigned occ = 1u << 12;       // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i)
-    bool opened = true;
-    if (occupied) {
+  for (int n0 = blockIdx.y * fpb; n0 < n1; n0 += OCC_CH) {
+    unsigned vcp = 0;                              // the centre values (<= 255) of OCC_CH frames, one byte each
 #pragma unroll
-      for (int pos = 6; pos <= 18; ++pos) {
-        if (!((OCC_INNER >> pos) & 1u) || pos == 12) continue;
-        if ((inside >> pos) & 1u)
-          if (is_occ(occ_sample(lab, tab[pos * 128 + threadIdx.x], cols), g.binary)) occ |= 1u << pos;
+    for (int c = 0; c < OCC_CH; ++c)               // a frame past the end repeats the last one (loads stay in bounds)
+      vcp |= occ_sample(labels, (unsigned)min(n0 + c, n1 - 1) * frame, ein[4], cols) << (8 * c);
+#pragma unroll 1
+    for (int c = 0; c < OCC_CH; ++c) {
+      const int n = n0 + c;
+      if (n >= n1) break;                          // block-uniform
+      const unsigned nb = (unsigned)n * frame;
+      unsigned v = (vcp >> (8 * c)) & 255u;
+      const bool occupied = live && is_occ(v, g.binary);
+      unsigned occ = 1u << 12;     // 5x5 occupancy mask around (ty, tx); bit (j*5+i) <-> (ty-2+j, tx-2+i)
+      bool opened = true;
+      if (occupied) {
+        // positions outside the template have all-zero entries: they sample 0, "not occupied", and are
+        // masked out by `inside` below
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          if (k == 4) continue;
+          if (is_occ(occ_sample(labels, nb, ein[k], cols), g.binary)) occ |= 1u << ((1 + k / 3) * 5 + 1 + k % 3);
+        }
+        opened = ((~occ) & inside & OCC_INNER) == 0;            // q = p: every in-template neighbour occupied
       }
-      opened = ((~occ) & inside & OCC_INNER) == 0;            // q = p: every in-template neighbour occupied
+      // The undecided cells (occupied, but not the centre of a full 3x3 block) need the outer ring.
+      // They are few, so the warp serves them two at a time: 16 lanes sample one outer pixel each,
+      // 9 lanes test one erosion centre each.
+      unsigned todo = __ballot_sync(0xffffffffu, occupied && !opened);
+      while (todo) {
+        const int s0 = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int s1 = todo ? __ffs(todo) - 1 : -1;
+        if (s1 >= 0) todo &= todo - 1;
+        const int src = half ? s1 : s0;
+        const bool helping = src >= 0;
+        const int srcl = helping ? src : s0;
+        const unsigned s_inside = __shfl_sync(0xffffffffu, inside, srcl);
+        const unsigned s_occ = __shfl_sync(0xffffffffu, occ, srcl);
+        unsigned bit = 0;
+        if (helping && ((s_inside >> my_outer) & 1u))
+          if (is_occ(occ_sample(labels, nb, my_outer_row[srcl], cols), g.binary)) bit = 1u << my_outer;
+        const unsigned all = s_occ | __reduce_or_sync(half_mask, bit);
+        // opened(p) = OR_q AND_{r in N3(q)} occ(r): dilate ignores q outside the template, erode ignores r outside
+        const bool ok = helping && my_q && (s_inside & my_q) && (((~all) & s_inside & my_nb) == 0);
+        const unsigned okb = __ballot_sync(0xffffffffu, ok);     // the owner may sit in the other half-warp
+        if (lane == s0) opened = (okb & 0xffffu) != 0;
+        if (lane == s1) opened = (okb >> 16) != 0;
+      }
+      if (occupied && !opened) v = 2;                   // bev.py:203-205
+      unsigned out;
+      if (g.raw_template) {
+        out = v;                                        // laserscan branch: the template itself (bev.py:209-212)
+      } else if (g.binary) {
+        const unsigned m = (v * 100u) & 255u;           // uint8 * 100 (bev.py:139-142)
+        out = (m == 0u) ? 255u : ((200u - m) & 255u);   // bev.py:143-144
+      } else {
+        if (v == 3u) v = 1u;                            // bev.py:242
+        out = (v == 0u) ? 255u : ((200u - ((v * 100u) & 255u)) & 255u);   // bev.py:244-245
+      }
+      if (live) grids[(size_t)n * cells + o] = (int8_t)out;
     }
-    // The undecided cells (occupied, but not the centre of a full 3x3 block) need the outer ring.
-    // They are few, so the warp serves them two at a time: 16 lanes sample one outer pixel each,
-    // 9 lanes test one erosion centre each.
-    unsigned todo = __ballot_sync(0xffffffffu, occupied && !opened);
-    while (todo) {
-      const int s0 = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int s1 = todo ? __ffs(todo) - 1 : -1;
-      if (s1 >= 0) todo &= todo - 1;
-      const int src = half ? s1 : s0;
-      const bool helping = src >= 0;
-      const int srcl = helping ? src : s0;
-      const unsigned s_inside = __shfl_sync(0xffffffffu, inside, srcl);
-      const unsigned s_occ = __shfl_sync(0xffffffffu, occ, srcl);
-      unsigned bit = 0;
-      if (helping && ((s_inside >> my_outer) & 1u))
-        if (is_occ(occ_sample(lab, tab[my_outer * 128 + (threadIdx.x & ~31) + srcl], cols), g.binary)) bit = 1u << my_outer;
-      const unsigned all = s_occ | __reduce_or_sync(half_mask, bit);
-      // opened(p) = OR_q AND_{r in N3(q)} occ(r): dilate ignores q outside the template, erode ignores r outside
-      const bool ok = helping && my_q && (s_inside & my_q) && (((~all) & s_inside & my_nb) == 0);
-      const unsigned okb = __ballot_sync(0xffffffffu, ok);     // the owner may sit in the other half-warp
-      if (lane == s0) opened = (okb & 0xffffu) != 0;
-      if (lane == s1) opened = (okb >> 16) != 0;
-    }
-    if (occupied && !opened) v = 2;                   // bev.py:203-205
-    int out;
-    if (g.raw_template) {
-      out = v;                                        // laserscan branch: the template itself (bev.py:209-212)
-    } else if (g.binary) {
-      int m = (v * 100) & 255;                        // uint8 * 100 (bev.py:139-142)
-      out = (m == 0) ? 255 : ((200 - m) & 255);       // bev.py:143-144
-    } else {
-      if (v == 3) v = 1;                              // bev.py:242
-      out = (v == 0) ? 255 : ((200 - ((v * 100) & 255)) & 255);   // bev.py:244-245
-    }
-    if (live) grids[(size_t)n * cells + o] = (int8_t)out;
   }
 }
 
-static constexpr int OCC_SMEM = 25 * 128 * (int)sizeof(uint4);   // 51 200 B
-
-// the > 48 KB opt-in is per device: bc_create calls this for its GPU
-cudaError_t prepare_occgrid() { return cudaFuncSetAttribute(k_occgrid, cudaFuncAttributeMaxDynamicSharedMemorySize, OCC_SMEM); }
+// kept for bc_create's per-device set-up list; the kernel no longer needs a shared-memory opt-in
+cudaError_t prepare_occgrid() { return cudaSuccess; }
 
 void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grids, cudaStream_t s) {
-  const int smem = OCC_SMEM;
   static const int fpb_env = getenv("BC_OCC_FPB") ? atoi(getenv("BC_OCC_FPB")) : 0;     // tuning knob, read once
   const int cell_blocks = (g.Hc * g.Wc + 127) / 128;
-  // Frames per block: small (4..12, see above), and chosen so that the grid is close to a whole number of waves
-  // of resident blocks (4 per SM: 51 KB of shared memory, 104 registers): with 8 frames per block a 256-frame
-  // batch is 2 528 blocks = 4.27 waves of 592, i.e. a fifth wave that is three quarters empty.
+  // Frames per block: a small multiple of OCC_CH, chosen so that the grid is close to a whole number of waves
+  // of resident blocks (OCC_MINB per SM)
   int fpb = fpb_env;
   if (fpb <= 0) {
     static int slots = 0;
@@ -335,18 +359,24 @@ void launch_occgrid(const uint8_t* labels, int B, const BevGeom& g, int8_t* grid
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      slots = 4 * sms;
+      slots = OCC_MINB * sms;
     }
     double best = -1.0;
-    for (int f = 4; f <= 12; ++f) {
+    for (int f = OCC_CH; f <= 4 * OCC_CH; f += OCC_CH) {
       const long long blocks = (long long)cell_blocks * ((B + f - 1) / f);
       const long long waves = (blocks + slots - 1) / slots;
-      const double eff = (double)blocks / (double)(waves * slots) * (blocks * (double)f >= (double)cell_blocks * B ? (double)cell_blocks * B / (blocks * (double)f) : 1.0);
+      const double eff = (double)blocks / (double)(waves * slots) * ((double)cell_blocks * B / (blocks * (double)f));
       if (eff > best + 1e-9) { best = eff; fpb = f; }
     }
   }
-  dim3 grid(cell_blocks, (B + fpb - 1) / fpb);
-  k_occgrid<<<grid, 128, smem, s>>>(labels, g, B, fpb, grids);
+  // the kernel indexes the label maps with 32-bit offsets: at most 4 GB of them per launch
+  const size_t frame = (size_t)g.in_rows * g.in_cols;
+  const int per_launch = (int)std::min<size_t>((size_t)B, 0xffffffffull / frame);
+  for (int b0 = 0; b0 < B; b0 += per_launch) {
+    const int nb = std::min(per_launch, B - b0);
+    dim3 grid(cell_blocks, (nb + fpb - 1) / fpb);
+    k_occgrid<<<grid, 128, 0, s>>>(labels + (size_t)b0 * frame, g, nb, fpb, grids + (size_t)b0 * g.Hc * g.Wc);
+  }
 }
 
 // ------------------------------------------------------------------ streaming gather flags
