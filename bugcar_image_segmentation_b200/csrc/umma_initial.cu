@@ -201,22 +201,34 @@ k_umma_initial(const __grid_constant__ InitParams p) {
 // byte: 0x64bb is the fp16 number 1024 + bb) and ONE packed subtraction of 1024 -- no integer-to-float
 // conversions, no per-byte extraction; the 3-channel max-pool is a packed byte maximum on the same
 // words.  K order (any order is legal as long as B uses the same): per window row ky the bytes
-// 0..7 (8 halves), then the three bytes 8, then the validity flags; K = 40, padded to 48.
-// The folded weights keep fp32 accuracy as three fp16 limbs of  w_k s_c 2^e(o)  with a per-output-
-// channel power of two e(o) that lifts the row into fp16's normal range; 2^-e(o) is folded into the
-// batch-norm scale of the epilogue.
+// 0..7 (8 halves), then the three bytes 8, then the validity flags.  Only the first image row / column has taps
+// in the padding, so the nine tap flags collapse into four columns -- (oy > 0 and ox > 0), (oy > 0), (ox > 0), 1 --
+// whose weights are the sums of the offset terms of the taps they stand for: K = 27 + 4 = 31 -> 32, two K steps.
+// The folded weights are U8_LIMBS fp16 limbs of  w_k s_c 2^e(o)  (22 significant bits with two limbs, far below
+// the 16-bit rounding of the block's output) with a per-output-channel power of two e(o) that lifts the row into
+// fp16's normal range; 2^-e(o) is folded into the batch-norm scale of the epilogue.  The kernel's time is set by
+// the number of MMAs per tile (N = 16 MMAs cost their fixed issue interval, not their flops; more resident CTAs
+// change nothing: 7, 8 and 9 per SM all measured 148 us with 9 MMAs per tile), hence K = 32 and two limbs: 4 MMAs.
 static constexpr int U8_A = 128 * 128;            // A tile: 128 rows x 64 fp16 (48 used)
 static constexpr int U8_W = 16 * 128;             // one limb of B: 16 rows x 64 fp16
-static constexpr int U8_K = 48;
+static constexpr int U8_K = 32;
+#ifndef BC_U8_LIMBS
+#define BC_U8_LIMBS 2
+#endif
+static constexpr int U8_LIMBS = BC_U8_LIMBS;
 static constexpr int U8_OFF_A = 0;
 static constexpr int U8_OFF_W = U8_A;
-static constexpr int U8_OFF_BAR = U8_OFF_W + 3 * U8_W;
+static constexpr int U8_OFF_BAR = U8_OFF_W + U8_LIMBS * U8_W;
 static constexpr int U8_SMEM = U8_OFF_BAR + 64;
-static constexpr int U8_MINB = 7;    // (a second A tile so that tile k+1 is built during tile k's MMAs, 5 CTAs/SM, measured 160 vs 150 us)
+#ifndef BC_U8_MINB
+#define BC_U8_MINB 7
+#endif
+static constexpr int U8_MINB = BC_U8_MINB;    // (a second A tile so that tile k+1 is built during tile k's MMAs, 5 CTAs/SM, measured 160 vs 150 us)
 
-// K index of window byte b (0..8) of row ky, and of the validity flag of tap (ky, kx)
+// K index of window byte b (0..8) of row ky, and of the validity column of tap (ky, kx):
+// 27: first row and first column (needs oy > 0 and ox > 0), 28: first row, 29: first column, 30: always valid
 __host__ __device__ constexpr int u8_k_byte(int ky, int b) { return b < 8 ? ky * 8 + b : 24 + ky; }
-__host__ __device__ constexpr int u8_k_valid(int ky, int kx) { return 28 + ky * 3 + kx; }
+__host__ __device__ constexpr int u8_k_valid(int ky, int kx) { return ky == 0 ? (kx == 0 ? 27 : 28) : (kx == 0 ? 29 : 30); }
 
 // bytes i and j of `w` as the fp16 pair (i in the low half)
 template <int I, int J>
@@ -242,19 +254,14 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
     mbar_init(bar(D_FULL0), 1);
     mbar_init(bar(W_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar(W_FULL), 3 * U8_W);
-    bulk_load(sbase + U8_OFF_W, p.wblob, 3 * U8_W, bar(W_FULL));
+    mbar_expect_tx(bar(W_FULL), U8_LIMBS * U8_W);
+    bulk_load(sbase + U8_OFF_W, p.wblob, U8_LIMBS * U8_W, bar(W_FULL));
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  } else {
-    // K columns 40..63 of this thread's A row are never written again: zero them once
-    const int m = (warp & 3) * 32 + lane;
-#pragma unroll
-    for (int j = 5; j < 8; ++j)
-      *reinterpret_cast<uint4*>(smem + U8_OFF_A + swz<128>((uint32_t)(m * 128 + j * 16))) = make_uint4(0u, 0u, 0u, 0u);
   }
+  // (the MMAs read K columns 0..31 of an A row only, and every tile writes all of them)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -271,7 +278,7 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       mbar_wait(bar(A_FULL0), k & 1);
       tc_fence_after();
 #pragma unroll
-      for (int limb = 0; limb < 3; ++limb)
+      for (int limb = 0; limb < U8_LIMBS; ++limb)
 #pragma unroll
         for (int kk = 0; kk < U8_K / 16; ++kk)
           umma_mma_e(tmem, dA0 + (uint64_t)(kk * 2), dB0 + (uint64_t)(limb * (U8_W >> 4) + kk * 2), IDESC, (limb | kk) != 0);
@@ -324,12 +331,11 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
         if (!p.pool2) mx4 = __vmaxu4(mx4, __vmaxu4(r0, __vmaxu4(p1, p2)));
         else if (ky > 0) mx4 = __vmaxu4(mx4, __vmaxu4(p1, p2));        // 2x2 s2 pool: window rows / columns 1..2
       }
-      // bytes 8 of the three rows, then the validity flags (1.0 = 0x3c00): only the first row / column of the
+      // bytes 8 of the three rows, then the validity columns (1.0 = 0x3c00): only the first row / column of the
       // image has taps in the padding (2*oy + 1 <= 255 and 2*ox + 1 <= 511 always are inside)
       const uint32_t vt = oy > 0 ? 0x3c00u : 0u, vl = ox > 0 ? 0x3c00u : 0u, vtl = (oy > 0 && ox > 0) ? 0x3c00u : 0u;
       const uint32_t b8a = bytes_to_h2<0, 2>(r2[0] | (r2[1] << 16)), b8b = bytes_to_h2<0, 1>(r2[2]) & 0xffffu;
-      *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 3 * 16))) = make_uint4(b8a, b8b, vtl | (vt << 16), vt | (vl << 16));
-      *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 4 * 16))) = make_uint4(0x3c003c00u, vl | (0x3c00u << 16), 0x3c00u, 0u);
+      *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 3 * 16))) = make_uint4(b8a, b8b | (vtl << 16), vt | (vl << 16), 0x3c00u);
       fence_proxy_async();
       mbar_arrive(bar(A_FULL0));
       return mx4;
@@ -370,12 +376,13 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
 }  // namespace BC_NS
 using namespace BC_NS;
 
-// B image of the uint8 form: three fp16 limbs of  w_k s_c 2^e(o)  (27 columns) and of
-// 2^e(o) sum_c w_(c,tap) t_c  (9 columns), rows = output channels, K order as the kernel builds A.
+// B image of the uint8 form: U8_LIMBS fp16 limbs of  w_k s_c 2^e(o)  (27 columns) and of
+// 2^e(o) sum_(taps of the column) sum_c w_(c,tap) t_c  (4 validity columns), rows = output channels, K order as
+// the kernel builds A.
 // w: [27][13] ((c*3+ky)*3+kx major, c in RGB order).  unscale[o] = 2^-e(o) (16 floats, 1 for the unused rows).
 bool Umma<act_t>::initial_build_u8(uint8_t** out, const float* w, float* unscale) {
   const double mean[3] = {0.485, 0.456, 0.406}, sd[3] = {0.229, 0.224, 0.225};   // models.py:17-18
-  std::vector<uint8_t> img(3 * U8_W, 0);
+  std::vector<uint8_t> img(U8_LIMBS * U8_W, 0);
   for (int o = 0; o < 16; ++o) unscale[o] = 1.f;
   for (int o = 0; o < 13; ++o) {
     double col[U8_K] = {0.0};
@@ -387,7 +394,7 @@ bool Umma<act_t>::initial_build_u8(uint8_t** out, const float* w, float* unscale
           col[u8_k_byte(ky, 3 * kx + 2 - c)] = (double)w[(c * 9 + tap) * 13 + o] / (256.0 * sd[c]);
           t += (double)w[(c * 9 + tap) * 13 + o] * (-mean[c] / sd[c]);
         }
-        col[u8_k_valid(ky, kx)] = t;
+        col[u8_k_valid(ky, kx)] += t;
       }
     double mxv = 0.0;
     for (double v : col) mxv = std::max(mxv, std::fabs(v));
@@ -397,7 +404,7 @@ bool Umma<act_t>::initial_build_u8(uint8_t** out, const float* w, float* unscale
     unscale[o] = (float)std::ldexp(1.0, -e);
     for (int k = 0; k < U8_K; ++k) {
       double v = std::ldexp(col[k], e);
-      for (int limb = 0; limb < 3; ++limb) {
+      for (int limb = 0; limb < U8_LIMBS; ++limb) {
         const __half hb = __float2half_rn((float)v);
         v -= (double)__half2float(hb);
         memcpy(img.data() + limb * U8_W + swz<128>((uint32_t)(o * 128 + k * 2)), &hb, 2);
