@@ -314,22 +314,30 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
         }
       }
     };
-    // builds the A row of the tile whose words are in w[]; returns the packed max-pool bytes (B, G, R)
-    auto build = [&]() -> uint32_t {
+    // builds the A row of the tile whose words are in w[]; returns the max-pool of the window as fp16: (B, G) and R.
+    // The pool runs on the fp16 pairs the A row is made of (one HMNMX2 per pair; a packed BYTE maximum is seven
+    // instructions on this architecture, and the nine of them were a third of this function): first across the
+    // window rows (the three rows hold the same pixel / channel at the same position), then across the pixels.
+    auto hmax2u = [](uint32_t a, uint32_t b) -> uint32_t {
+      const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    };
+    auto build = [&]() -> uint2 {
       uint8_t* A = smem + U8_OFF_A;
       const int sh = ((6 * ox - 3) & 3) * 8;            // 8 or 24
-      uint32_t r2[3], mx4 = 0u;
+      uint32_t r2[3], mh[4] = {0u, 0u, 0u, 0u};         // mh: window bytes (0,1) (2,3) (4,5) (6,7), maximum over the rows
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         // window bytes 0-3, 4-7, 8 (B G R of the three pixels, in memory order)
         const uint32_t r0 = __funnelshift_r(w[3 * ky], w[3 * ky + 1], sh), r1 = __funnelshift_r(w[3 * ky + 1], w[3 * ky + 2], sh);
         r2[ky] = (w[3 * ky + 2] >> sh) & 0xffu;
-        *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + ky * 16))) =
-            make_uint4(bytes_to_h2<0, 1>(r0), bytes_to_h2<2, 3>(r0), bytes_to_h2<0, 1>(r1), bytes_to_h2<2, 3>(r1));
-        // max-pool: bytes 0-2 of (r0, the window from byte 3, the window from byte 6) are the three pixels' B G R
-        const uint32_t p1 = __funnelshift_r(r0, r1, 24), p2 = __funnelshift_r(r1, r2[ky], 16);
-        if (!p.pool2) mx4 = __vmaxu4(mx4, __vmaxu4(r0, __vmaxu4(p1, p2)));
-        else if (ky > 0) mx4 = __vmaxu4(mx4, __vmaxu4(p1, p2));        // 2x2 s2 pool: window rows / columns 1..2
+        const uint4 h = make_uint4(bytes_to_h2<0, 1>(r0), bytes_to_h2<2, 3>(r0), bytes_to_h2<0, 1>(r1), bytes_to_h2<2, 3>(r1));
+        *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + ky * 16))) = h;
+        if (ky == 0) {
+          if (!p.pool2) { mh[0] = h.x; mh[1] = h.y; mh[2] = h.z; mh[3] = h.w; }     // 2x2 s2 pool: window rows 1..2 only
+        } else {
+          mh[0] = hmax2u(mh[0], h.x); mh[1] = hmax2u(mh[1], h.y); mh[2] = hmax2u(mh[2], h.z); mh[3] = hmax2u(mh[3], h.w);
+        }
       }
       // bytes 8 of the three rows, then the validity columns (1.0 = 0x3c00): only the first row / column of the
       // image has taps in the padding (2*oy + 1 <= 255 and 2*ox + 1 <= 511 always are inside)
@@ -338,13 +346,19 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
       *reinterpret_cast<uint4*>(A + swz<128>((uint32_t)(m * 128 + 3 * 16))) = make_uint4(b8a, b8b | (vtl << 16), vt | (vl << 16), 0x3c00u);
       fence_proxy_async();
       mbar_arrive(bar(A_FULL0));
-      return mx4;
+      // across the pixels: B = max(b0, b3, b6), G = max(b1, b4, b7), R = max(b2, b5, b8); the 2x2 pool leaves out
+      // pixel 0 (b0..b2) and row 0 (zero is the identity: the values are bytes)
+      const uint32_t px0 = p.pool2 ? 0u : 0xffffffffu;
+      const uint32_t bg = hmax2u(hmax2u(mh[0] & px0, __byte_perm(mh[1], mh[2], 0x5432)), mh[3]);      // (b3, b4)
+      const uint32_t r8 = hmax2u(p.pool2 ? (b8a & 0xffff0000u) : b8a, __byte_perm(b8b, 0u, 0x1010));  // (b8 rows 0 1) vs (row 2, row 2)
+      const uint32_t rr = hmax2u(__byte_perm(mh[1] & px0, mh[2], 0x7610), r8);                        // (b2, b5)
+      return make_uint2(bg, hmax2u(rr, rr >> 16));
     };
     if (T > 0) fetch(0);
     for (int k = 0; k < T; ++k) {
       // (the MMAs of tile k-1 have finished reading A: this thread passed its D_FULL wait below)
       const int pix_cur = pix;
-      const uint32_t mx_cur = build();
+      const uint2 mx_cur = build();
       if (k + 1 < T) fetch(k + 1);
       // ---- epilogue of tile k: BN (with the weights' power-of-two un-scale folded in) + PReLU on the 13 conv
       // channels; the 3 pooled channels: max-pool of the normalised image = normalisation of the max byte (the
@@ -357,8 +371,13 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
 #pragma unroll
       for (int o = 0; o < 13; ++o) r[o] = prelu_f(fmaf(r[o], p.fu8[o], p.f[16 + o]), p.f[32 + o]);
 #pragma unroll
-      for (int c = 0; c < 3; ++c)                      // RGB order: byte 2 - c of the packed maximum
-        r[13 + c] = prelu_f(fmaf((float)((mx_cur >> (8 * (2 - c))) & 0xffu), p.fpool[c], p.fpool[3 + c]), p.f[32 + 13 + c]);
+      {                                                // RGB order: R, then G and B of the (B, G) pair
+        const float2 bgf = __half22float2(*reinterpret_cast<const __half2*>(&mx_cur.x));
+        const float mxf[3] = {__half2float(__ushort_as_half((unsigned short)(mx_cur.y & 0xffffu))), bgf.y, bgf.x};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          r[13 + c] = prelu_f(fmaf(mxf[c], p.fpool[c], p.fpool[3 + c]), p.f[32 + 13 + c]);
+      }
       uint4* o = reinterpret_cast<uint4*>(p.out + (size_t)pix_cur * 16);
       o[0] = pack8(r);
       o[1] = pack8(r + 8);
