@@ -182,7 +182,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[S::NBARS];
   uint32_t* xfills = tmem_slot + 2;                    // [NX] refills issued per x buffer (see epilogue 2)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index made provably warp-uniform: role branches become uniform branches
 
   // ---- one-time setup: barriers, weights + parameters to smem (two bulk copies), TMEM
   if (tid == 0) {

@@ -67,7 +67,7 @@ k_umma_down(const __grid_constant__ CUtensorMap map_x,   // 5D [n*Ho][2][Wo][2][
   enum { TAP_FULL = 0, TAP_EMPTY, D_FULL0, D_FULL1, D_EMPTY0, D_EMPTY1, W_FULL, NBARS };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index made provably warp-uniform: role branches become uniform branches
 
   if (tid == 0) {
     mbar_init(bar(TAP_FULL), 1);

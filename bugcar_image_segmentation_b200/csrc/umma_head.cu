@@ -82,7 +82,7 @@ k_umma_head(const __grid_constant__ CUtensorMap map_x,   // 4D [N][128][256][16]
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
   uint8_t* slut = smem + HEAD_OFF_LUT;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index made provably warp-uniform: role branches become uniform branches
 
   if (tid == 0) {
     for (int b = 0; b < 2 * HEAD_STAGES; ++b) mbar_init(bar(TAP_FULL0 + b), 1);

@@ -68,7 +68,7 @@ k_umma_initial(const __grid_constant__ InitParams p) {
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
   float* slut = (float*)(smem + INIT_OFF_LUT);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index made provably warp-uniform: role branches become uniform branches
 
   if (tid == 0) {
     mbar_init(bar(A_FULL), 128);
@@ -247,7 +247,7 @@ k_umma_initial_u8(const __grid_constant__ InitParams p) {
   enum { A_FULL0 = 0, D_FULL0, W_FULL, NBARS };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index made provably warp-uniform: role branches become uniform branches
 
   if (tid == 0) {
     mbar_init(bar(A_FULL0), 128);

@@ -94,7 +94,7 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
          DD_FULL, W_FULL, NBARS };
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
   uint32_t* tmem_slot = (uint32_t*)&bars[NBARS];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp index made provably warp-uniform: role branches become uniform branches
 
   if (tid == 0) {
     const int one[] = {X_FULL0, X_FULL1, X_EMPTY0, X_EMPTY1, DA_FULL, DB_FULL, DC_FULL, OUT_EMPTY, DD_FULL, W_FULL};
