@@ -35,6 +35,7 @@ namespace BC_NS {
 
 // =================================================================== the kernel
 struct UmmaParams {
+  uint64_t pol_x, pol_y, pol_e1, pol_e1n;   // L2 eviction-priority hints: x loads, y stores, e1 tap loads, e1' stores
   int num_tiles;        // 128-pixel tiles in this launch
   int tiles_per_frame;  // H*W/128
   int rows_per_tile;    // image rows a tile spans (128 / W)
@@ -240,11 +241,11 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         const int tile = tile_of(k);
         if constexpr (NARROW) {
           mbar_expect_tx_e(bar(S::X_FULL + k), S::RBUF);
-          tma_load_2d_e(sbase + S::OFF_R + k * S::RBUF, &map_x, 0, tile * 128, bar(S::X_FULL + k));
+          tma_load_2d_e(sbase + S::OFF_R + k * S::RBUF, &map_x, 0, tile * 128, bar(S::X_FULL + k), p.pol_x);
         } else {
           mbar_expect_tx_e(bar(S::X_FULL + k), S::XBUF);
           for (int s = 0; s < S::NSUB; ++s)
-            tma_load_2d_e(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k));
+            tma_load_2d_e(sbase + S::OFF_X + k * S::XBUF + s * S::XSUB, &map_x, s * 64, tile * 128, bar(S::X_FULL + k), p.pol_x);
         }
       }
     int slot = 0, round = 0;
@@ -257,7 +258,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         // vertical taps of a full-width tile: rows y0-2 .. y0+3 arrive as one box (three ring slots), tap ky starts ky rows in
         if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
         mbar_expect_tx_e(bar(S::TAP_FULL + slot), 3 * S::TAP_BYTES);
-        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, 0, y0 - 2, n, bar(S::TAP_FULL + slot));
+        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, 0, y0 - 2, n, bar(S::TAP_FULL + slot), p.pol_e1);
         slot += 3;
         if (slot == S::NRING) { slot = 0; ++round; }
       } else if (CI == 32 && !CONV && p.pairslab) {
@@ -272,7 +273,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
           if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
           mbar_expect_tx_e(bar(S::TAP_FULL + slot), bytes);
           tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::PAIR_SLOT, &map_e1, 0, y0 + (nky == 3 ? (ky - 1) * p.pair_step : 0),
-                        -p.pair_halo, n, bar(S::TAP_FULL + slot));
+                        -p.pair_halo, n, bar(S::TAP_FULL + slot), p.pol_e1);
           if (++slot == S::NRING_PAIR) { slot = 0; ++round; }
         }
       } else if (CI == 16 && p.rowslab) {
@@ -281,14 +282,14 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         for (int ky = 0; ky < 3; ++ky) {
           if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
           mbar_expect_tx_e(bar(S::TAP_FULL + slot), S::ROW_BYTES);
-          tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, -1, y0 + ky - 1, n, bar(S::TAP_FULL + slot));
+          tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, -1, y0 + ky - 1, n, bar(S::TAP_FULL + slot), p.pol_e1);
           if (++slot == S::NRING) { slot = 0; ++round; }
         }
       } else
       for (int t = 0; t < p.ntaps; ++t) {
         if (round >= 1) mbar_wait(bar(S::TAP_EMPTY + slot), (round - 1) & 1);
         mbar_expect_tx_e(bar(S::TAP_FULL + slot), S::TAP_BYTES);
-        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot));
+        tma_load_4d_e(sbase + S::OFF_TAPS + slot * S::SLOT_BYTES, &map_e1, 0, p.dx[t], y0 + p.dy[t], n, bar(S::TAP_FULL + slot), p.pol_e1);
         if (++slot == S::NRING) { slot = 0; ++round; }
       }
       if (p.reverse) {
@@ -469,7 +470,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile_of(k) * 128 + m) * CI + EH * CI1);
 #pragma unroll
         for (int c = 0; c < CI1 / 8; ++c)
-          o[c] = pack8(v + 8 * c);
+          st_global_hint(o + c, pack8(v + 8 * c), p.pol_e1n);
       } else {
 #pragma unroll
         for (int c = 0; c < CI1 / 8; ++c)
@@ -544,13 +545,13 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
       if (storer) {
         mbar_wait(bar(S::Y_FULL + grp), par);
         for (int s = 0; s < S::NSUB; ++s)
-          tma_store_2d(&map_y, smem_u32(yt) + s * S::XSUB, s * 64, tile * 128);
+          tma_store_2d(&map_y, smem_u32(yt) + s * S::XSUB, s * 64, tile * 128, p.pol_y);
         tma_store_commit();
         if constexpr (NARROW) {                       // every thread has read the residual tile: refill it
           if (k + NX < T) {
             const int nt = tile_of(k + NX);
             mbar_expect_tx(bar(S::X_FULL + xb), S::RBUF);
-            tma_load_2d(sbase + S::OFF_R + xb * S::RBUF, &map_x, 0, nt * 128, bar(S::X_FULL + xb));
+            tma_load_2d(sbase + S::OFF_R + xb * S::RBUF, &map_x, 0, nt * 128, bar(S::X_FULL + xb), p.pol_x);
             asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&xfills[xb])), "r"((uint32_t)((k + NX) / NX)) : "memory");
           }
         }
@@ -573,7 +574,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
         uint4* o = reinterpret_cast<uint4*>(p.out_small + ((size_t)tile * 128 + m) * CN + EH * CN1);
 #pragma unroll
         for (int c = 0; c < CN1 / 8; ++c)
-          o[c] = pack8(v + 8 * c);
+          st_global_hint(o + c, pack8(v + 8 * c), p.pol_e1n);
       }
       // The y buffer may be overwritten once the store has read it (and the projection MMAs, which
       // the D3_FULL wait above covers, have consumed it).  In place: the thread that knows first
@@ -586,7 +587,7 @@ k_umma_bottleneck(const __grid_constant__ CUtensorMap map_e1,   // 4D [N][H][W][
             const int nt = tile_of(k + NX);
             mbar_expect_tx(bar(S::X_FULL + xb), S::XBUF);
             for (int s = 0; s < S::NSUB; ++s)
-              tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb));
+              tma_load_2d(sbase + S::OFF_X + xb * S::XBUF + s * S::XSUB, &map_x, s * 64, nt * 128, bar(S::X_FULL + xb), p.pol_x);
             asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&xfills[xb])), "r"((uint32_t)((k + NX) / NX)) : "memory");
           }
         }
@@ -806,6 +807,16 @@ static cudaError_t launch_one(const UmmaPack& pk, const act_t* e1, const act_t* 
   p.pair_step = pair_step;
   p.pair_halo = pair_halo;
   p.reverse = g_umma_reverse;
+  {
+    // BC_L2_HINTS = four letters (n normal, f evict-first, l evict-last) for: x loads, y stores, e1 tap loads, e1' stores
+    static const uint64_t* pol = [] {
+      static uint64_t v[4] = {L2_EVICT_NORMAL, L2_EVICT_NORMAL, L2_EVICT_NORMAL, L2_EVICT_NORMAL};
+      const char* e = getenv("BC_L2_HINTS");
+      for (int i = 0; e && i < 4 && e[i]; ++i) v[i] = e[i] == 'f' ? L2_EVICT_FIRST : e[i] == 'l' ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+      return v;
+    }();
+    p.pol_x = pol[0]; p.pol_y = pol[1]; p.pol_e1 = pol[2]; p.pol_e1n = pol[3];
+  }
   p.has_next = has_next;
   p.out_small = out_small;
   p.wblob = pk.wblob;

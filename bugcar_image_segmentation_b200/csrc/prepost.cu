@@ -8,8 +8,8 @@
 //       k_occgrid       per frame: bilinear label blend + 3x3 open + int8 map,
 //                       one kernel, no intermediate image              bev.py:166-246 / 97-144
 //
-// All of it is byte/integer arithmetic with fp64 coordinates, bound by HBM/L2 traffic
-// (K9: 131 072 B labels in, Hc*Wc B out per frame).  Semantics follow OpenCV 4.x as
+// All of it is byte/integer arithmetic with fp64 coordinates (K9: 131 072 B labels in, Hc*Wc B out per
+// frame; a gather of up to 25 x 4 label bytes per cell, bound by load latency and issue slots, not by HBM).  Semantics follow OpenCV 4.x as
 // restated (and pinned against cv2) in oracle/cv_ops.py.
 #include "internal.h"
 

@@ -96,7 +96,8 @@ int bc_set_host_overlap(bc_ctx* ctx, int enable);
 /* Replaces bev_transform_tools.__init__/fromJSON state (bev.py:13-41): src->dst
  * homography `h_M` (row-major 3x3, bev.py:31-32), label-map shape (rows, cols)
  * ("input image size", bev.py:30,169), warped size (ww, wh) ("output image size",
- * bev.py:29) and cm_per_px (bev.py:35). */
+ * bev.py:29) and cm_per_px (bev.py:35).  The label map must be 2..32767 pixels per side (the
+ * occupancy-grid kernel samples fixed 2x2 blocks of label pixels); BC_ERR_ARG otherwise. */
 int bc_set_bev(bc_ctx* ctx, const double h_M[9], int in_rows, int in_cols,
                int warp_w, int warp_h, double cm_per_px);
 

@@ -140,6 +140,39 @@ def test_grid_fuzz_vs_oracle_batched_and_ros(ctx):
                 assert np.array_equal(ros[i].reshape(-1), bev_oracle.ros_layout(want)), (it, binary, i)
 
 
+def test_grid_tiny_label_maps_every_footprint_on_a_border(ctx):
+    """K9 samples fixed 2 x 2 blocks of label pixels with the border taps folded into the weights (prepost.cu
+    k_occ_table): label maps of 2..9 pixels per side under shifted / scaled homographies put every case of that
+    folding (footprint one pixel before the first or on the last row / column, fully outside) into play."""
+    import torch
+    from oracle import bev_oracle
+    rng = np.random.default_rng(5)
+    for it in range(24):
+        rows, cols = int(rng.integers(2, 10)), int(rng.integers(2, 10))
+        ww, wh = int(rng.integers(20, 60)), int(rng.integers(20, 60))
+        # source rectangle a little larger than the image (so the warp reads past all four borders), jittered
+        quad = np.array([[-1.5, -1.5], [cols + 0.5, -1.5], [cols + 0.5, rows + 0.5], [-1.5, rows + 0.5]], np.float64)
+        quad += rng.normal(0, 0.4, (4, 2))
+        dst = np.array([[0, 0], [ww, 0], [ww, wh], [0, wh]], np.float64)
+        M = synth.perspective_transform(quad, dst)
+        cm = float(rng.choice([2, 4, 5]))
+        cell = float(rng.choice([0.05, 0.1, 0.2]))
+        w_m, h_m = ww * cm / 100.0 * float(rng.uniform(0.6, 1.0)), wh * cm / 100.0 * float(rng.uniform(0.6, 1.0))
+        labs = rng.integers(0, 4, (2, rows, cols)).astype(np.uint8)
+        ctx.set_bev(M.reshape(-1), rows, cols, ww, wh, cm)
+        try:
+            hc, wc = ctx.occgrid_shape(w_m, h_m, cell)
+        except Exception:
+            continue                                        # empty grid request
+        d = torch.from_numpy(labs).cuda()
+        for binary in (0, 1):
+            out = torch.empty((2, hc, wc), dtype=torch.int8, device="cuda")
+            ctx.occgrid(d, 2, w_m, h_m, cell, binary, 0, out)
+            for i in range(2):
+                want = bev_oracle.occupancy_grid(labs[i], M, ww, wh, cm, w_m, h_m, cell, binary=bool(binary))
+                assert np.array_equal(out[i].cpu().numpy(), want), (it, rows, cols, binary, i)
+
+
 def test_grid_error_behaviour(tmp_path):
     from bugcar_image_segmentation_b200 import _lib
     bev, c, rows, cols = _bev("A")
@@ -153,6 +186,9 @@ def test_grid_error_behaviour(tmp_path):
     with pytest.raises(_lib.BugcarError) as e:              # calibration not set
         raw.occgrid_shape(10.0, 10.0, 0.1)
     assert e.value.code == _lib.BC_ERR_STATE
+    with pytest.raises(_lib.BugcarError) as e:              # a label map needs two pixels per side (include/bugcar_b200.h)
+        raw.set_bev(np.eye(3).reshape(-1), 1, 512, 500, 500, 2.0)
+    assert e.value.code == _lib.BC_ERR_ARG
     with pytest.raises(_lib.BugcarError) as e:              # weights not loaded
         raw.enet_labels(1, 0, 1, np.zeros(256, np.uint8), 1)
     assert e.value.code == _lib.BC_ERR_STATE
