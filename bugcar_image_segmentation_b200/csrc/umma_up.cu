@@ -32,6 +32,9 @@ struct UpParams {
   float f[384];
 };
 
+#ifndef BC_UP5_MINB
+#define BC_UP5_MINB 4
+#endif
 template <int CIN, int CI, int COUT>
 struct UpSmem {
   static constexpr int RB = CI * 2;                    // row bytes of CI-wide operands
@@ -48,9 +51,10 @@ struct UpSmem {
   static constexpr int WT_BYTES = 4 * CI * RB;
   static constexpr int W3_BYTES = COUT * RB;
   static constexpr int W1N_BYTES = 16 * 128;           // next projection [16][64] (COUT == 64 only)
-  // upsample5_0 (COUT = 16) is small enough for three CTAs per SM with one x buffer and D_c aliased
-  // onto D_b (dead once epilogue B has read it); upsample4_0 fills the SM with one CTA
-  static constexpr int MINB = COUT == 16 ? 3 : 1;
+  // upsample5_0 (COUT = 16) is small enough for four CTAs per SM with one x buffer, D_c aliased onto D_b (dead
+  // once epilogue B has read it) and the staged output rows aliased onto the e2 tiles (dead once G3 has read them;
+  // epilogue B of the next tile waits for the TMA store to have read the rows); upsample4_0 fills the SM with one CTA
+  static constexpr int MINB = COUT == 16 ? BC_UP5_MINB : 1;
   // upsample4_0 keeps ONE tile in flight per SM, so its four epilogues are the critical path: two warps per TMEM
   // lane quarter, each taking half of the columns / taps / rows of every epilogue
   static constexpr int EPW = COUT == 64 ? 2 : 1;
@@ -59,8 +63,10 @@ struct UpSmem {
   static constexpr int OFF_X = 0;
   static constexpr int OFF_E1 = OFF_X + NXB * XBUF;
   static constexpr int OFF_E2 = OFF_E1 + ((E_TILE + 1023) / 1024) * 1024;
-  static constexpr int OFF_OUT = OFF_E2 + 4 * E_TILE;
-  static constexpr int OFF_W = OFF_OUT + OUT_BYTES;
+  static constexpr bool OUT_ON_E2 = COUT == 16 && MINB >= 4;
+  static_assert(!OUT_ON_E2 || OUT_BYTES <= 4 * E_TILE, "staged rows must fit over the e2 tiles");
+  static constexpr int OFF_OUT = OUT_ON_E2 ? OFF_E2 : OFF_E2 + 4 * E_TILE;
+  static constexpr int OFF_W = OUT_ON_E2 ? OFF_E2 + 4 * E_TILE : OFF_OUT + OUT_BYTES;
   static constexpr int OFF_B1 = OFF_W;
   static constexpr int OFF_WT = OFF_B1 + ((NSUB * B1_SUB + 1023) / 1024) * 1024;
   static constexpr int OFF_W3 = OFF_WT + ((WT_BYTES + 1023) / 1024) * 1024;
@@ -215,6 +221,9 @@ k_umma_up(const __grid_constant__ CUtensorMap map_x,   // 2D [low px][CIN], box 
       mbar_arrive(bar(E1_FULL));
       // ---- E_B: e2_t = act(tconv tap + bt) -> 4 smem tiles
       mbar_wait(bar(DB_FULL), k & 1);
+      if constexpr (S::OUT_ON_E2) {                     // the previous tile's staged rows lie here until the TMA store has read them
+        if (k >= 1) mbar_wait(bar(OUT_EMPTY), (k - 1) & 1);
+      }
       tc_fence_after();
 #pragma unroll 1
       for (int t = (S::EPW == 2 ? 2 * eh : 0); t < (S::EPW == 2 ? 2 * eh + 2 : 4); ++t) {
