@@ -169,8 +169,9 @@ def test_labels_same_for_all_input_kinds_and_chunks(setup):
     # fp64 / fp32 NCHW inputs take the same kernel with the same fp32 operands: identical labels
     from_f64 = m.predict(setup["x"])
     assert np.array_equal(m.predict(setup["x"].astype(np.float32)), from_f64)
-    # uint8 frames fold the normalisation into the weights (s*u + t, exact bytes as operands): equal to
-    # the float path up to fp32 round-off, i.e. labels may differ only at 16-bit rounding ties
+    # uint8 frames fold the normalisation into the weights (s*u + t, exact bytes as operands, two fp16 weight
+    # limbs = 22 significant bits): equal to the float path far below the 16-bit rounding of the block's output,
+    # i.e. labels may differ only at 16-bit rounding ties
     # (the random-weight net is chaotic -- a one-ulp 16-bit flip in the first block moves max-pool indices
     # downstream -- so only the trained-like weights give a meaningful bound)
     assert (from_f64 == base).mean() >= (0.9995 if setup["which"] == "trained" else 0.9), (from_f64 == base).mean()
@@ -238,7 +239,7 @@ def test_pipeline_resizes_camera_frames(setup):
     staged = np.stack([bev.create_occupancy_grid(s, 10.0, 10.0, 0.1) for s in seg])
     fused = FramePipeline(m, bev, 10.0, 10.0, 0.1)(frames)
     # the staged calls feed ENet the fp64 tensor of ENET.preprocess, the fused path folds the normalisation into
-    # the first conv (raw bytes as operands): same numbers up to fp32 round-off, so labels / cells can differ only
+    # the first conv (raw bytes as operands): same numbers to about 2^-22, so labels / cells can differ only
     # at bf16 rounding ties (chaotic random-weight net: loose bound, see the input-kinds test)
     same = (fused == staged).mean()
     # (trained-like weights on these out-of-distribution blocky frames: 99.6 % of the cells identical, the same
